@@ -1,0 +1,186 @@
+// dan_capi.cu — the extern "C" boundary declared in include/dan_b200.h.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include "dan_internal.h"
+
+namespace {
+thread_local char g_error[512] = "";
+thread_local int g_launches = 0;
+}  // namespace
+
+void dan_set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+void dan_count_launch(int n) { g_launches += n; }
+
+extern "C" {
+
+const char* dan_last_error(void) { return g_error; }
+const char* dan_version(void) { return "dan_b200 0.1 sm_100a"; }
+int dan_last_launch_count(void) { return g_launches; }
+
+int dan_model_create(const dan_config* cfg, dan_model** out) {
+  if (!cfg || !out) { dan_set_error("null argument"); return DAN_E_INVALID; }
+  *out = nullptr;
+  const dan_config& c = *cfg;
+  if (c.total_conv_layers < 1 || c.total_conv_layers > DAN_MAX_LAYERS) { dan_set_error("total_conv_layers %d out of range 1..%d", c.total_conv_layers, DAN_MAX_LAYERS); return DAN_E_UNSUPPORTED; }
+  if (c.channels < 16 || c.channels % 16) { dan_set_error("channels must be a multiple of 16 (got %d)", c.channels); return DAN_E_UNSUPPORTED; }
+  if (c.embed_dim < 1 || c.embed_dim > 64) { dan_set_error("embed_dim %d unsupported", c.embed_dim); return DAN_E_UNSUPPORTED; }
+  if (c.num_fc < 1 || c.num_fc > DAN_MAX_FC) { dan_set_error("layer_sizes must have 1..%d entries", DAN_MAX_FC); return DAN_E_UNSUPPORTED; }
+  for (int i = 0; i < c.num_fc; ++i)
+    if (c.fc_sizes[i] < 16 || c.fc_sizes[i] % 16) { dan_set_error("FC width %d must be a multiple of 16", c.fc_sizes[i]); return DAN_E_UNSUPPORTED; }
+  if (c.highway && (c.bottleneck < 16 || c.bottleneck % 16 || c.bottleneck > 64)) { dan_set_error("bottleneck size must be 16, 32, 48 or 64 (got %d)", c.bottleneck); return DAN_E_UNSUPPORTED; }
+  if (c.num_reads < 1 || c.read_len < 3) { dan_set_error("bad pileup shape %d x %d", c.num_reads, c.read_len); return DAN_E_INVALID; }
+  if (c.pool_combine_dimension < 0 || (c.pool_combine_dimension % 16)) { dan_set_error("pool_combine_dimension must be a multiple of 16"); return DAN_E_UNSUPPORTED; }
+  int gap = 1;
+  for (int l = 0; l < c.total_conv_layers; ++l) {
+    if (c.dilation[l] < 1 || c.dilation[l] > 8) { dan_set_error("dilation %d of layer %d unsupported (1..8)", c.dilation[l], l + 1); return DAN_E_UNSUPPORTED; }
+    if (c.dilation[l] > gap) gap = c.dilation[l];
+    if (c.is_residual[l] && l == 0) { dan_set_error("layer 1 cannot be residual (channel mismatch; model.py:28,209)"); return DAN_E_UNSUPPORTED; }
+  }
+  if (c.pool_after[c.total_conv_layers - 1]) { /* harmless: pooled after the last layer is never consumed */ }
+  dan_model* m = new (std::nothrow) dan_model();
+  if (!m) { dan_set_error("out of host memory"); return DAN_E_INVALID; }
+  memset(m, 0, sizeof(*m));
+  m->cfg = c;
+  if (cudaGetDevice(&m->device) != cudaSuccess) { delete m; dan_set_error("no CUDA device"); return DAN_E_CUDA; }
+  m->L = c.total_conv_layers; m->C = c.channels; m->bott = c.highway ? c.bottleneck : 0;
+  m->P = c.read_len; m->R = c.num_reads;
+  m->Cin = 2 * c.embed_dim + (c.use_q_scores ? 1 : 0) + (c.use_strands ? 1 : 0) + (c.use_reads_ref_var_mask ? 3 : 0);
+  m->CinPad = round_up_i(m->Cin, 16);
+  m->geom.P = m->P; m->geom.R = m->R; m->geom.gap = gap; m->geom.pitch = m->P + gap;
+  m->pooled = (c.skip_final_maxpool ? 1 : 2) * m->C * m->P;
+  m->pooledPad = round_up_i(m->pooled, 16);
+  m->hwFeat = c.highway ? (c.concat_hw_reads ? m->L : 1) * m->bott * m->R : 0;
+  m->fcIn = (c.pool_combine_dimension > 0 ? c.pool_combine_dimension : m->pooled) + m->hwFeat;
+  m->fcInPad = round_up_i(m->fcIn, 16);
+  m->hidden = c.fc_sizes[c.num_fc - 1];
+  m->pass_candidates = 8;
+  *out = m;
+  return DAN_OK;
+}
+
+int dan_model_destroy(dan_model* m) {
+  if (!m) return DAN_OK;
+  dan_fp32_free(m);
+  dan_bf16_free(m);
+  delete m;
+  return DAN_OK;
+}
+
+int dan_model_load_weights(dan_model* m, const dan_weights* w, void* stream) {
+  if (!m || !w) { dan_set_error("null argument"); return DAN_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int rc = dan_fp32_pack(m, w, st);
+  if (rc) return rc;
+  if (dan_bf16_supported(m)) {
+    rc = dan_bf16_pack(m, w, st);
+    if (rc) return rc;
+  }
+  m->loaded = true;
+  return DAN_OK;
+}
+
+int dan_model_set_pass_candidates(dan_model* m, int candidates) {
+  if (!m || candidates < 1) { dan_set_error("pass_candidates must be >= 1"); return DAN_E_INVALID; }
+  m->pass_candidates = candidates;
+  return DAN_OK;
+}
+
+size_t dan_workspace_bytes(const dan_model* m, int batch, int precision) {
+  if (!m || batch < 0) return 0;
+  if (precision == DAN_PRECISION_BF16) return dan_bf16_workspace_bytes(m, batch);
+  return dan_fp32_workspace_bytes(m, batch);
+}
+
+static int check_forward_args(dan_model* m, int precision, const uint8_t* reads, const uint8_t* q, const uint8_t* s,
+                              const uint8_t* ref, const uint8_t* rm, const uint8_t* vm, int batch, const void* out) {
+  if (!m) { dan_set_error("null model"); return DAN_E_INVALID; }
+  if (!m->loaded) { dan_set_error("dan_model_load_weights has not been called"); return DAN_E_INVALID; }
+  if (batch < 0) { dan_set_error("negative batch"); return DAN_E_INVALID; }
+  if (batch > 0 && (!reads || !ref || !out)) { dan_set_error("reads / ref / output pointer is null"); return DAN_E_INVALID; }
+  if (batch > 0 && m->cfg.use_q_scores && !q) { dan_set_error("model uses q-scores but q_scores is null (model.py:534)"); return DAN_E_INVALID; }
+  if (batch > 0 && m->cfg.use_strands && !s) { dan_set_error("model uses strands but strands is null (model.py:549)"); return DAN_E_INVALID; }
+  if (batch > 0 && m->cfg.use_reads_ref_var_mask && (!rm || !vm)) { dan_set_error("model uses ref/var masks but a mask pointer is null (model.py:576)"); return DAN_E_INVALID; }
+  if (precision != DAN_PRECISION_FP32 && precision != DAN_PRECISION_BF16) { dan_set_error("unknown precision %d", precision); return DAN_E_INVALID; }
+  if (precision == DAN_PRECISION_BF16 && !dan_bf16_supported(m)) { dan_set_error("bf16 tcgen05 path does not cover this configuration"); return DAN_E_UNSUPPORTED; }
+  return DAN_OK;
+}
+
+int dan_forward(dan_model* m, int precision, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
+                const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks, int batch, float* heads_out,
+                void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  int rc = check_forward_args(m, precision, reads, q_scores, strands, ref, ref_masks, var_masks, batch, heads_out);
+  if (rc) return rc;
+  if (batch == 0) return DAN_OK;
+  if (!workspace) { dan_set_error("null workspace"); return DAN_E_WORKSPACE; }
+  DevInputs in{reads, q_scores, strands, ref, ref_masks, var_masks};
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == DAN_PRECISION_BF16) return dan_bf16_forward(m, in, batch, heads_out, workspace, workspace_bytes, st);
+  return dan_fp32_forward(m, in, batch, heads_out, workspace, workspace_bytes, st);
+}
+
+static size_t host_stage_bytes(const dan_model* m, int batch) {
+  const size_t tile = (size_t)batch * m->P * m->R, vec = (size_t)batch * m->P;
+  return 3 * round_up_z(tile, 256) + 3 * round_up_z(vec, 256) + round_up_z((size_t)batch * DAN_NUM_HEAD_OUTPUTS * 4, 256);
+}
+
+size_t dan_workspace_bytes_host(const dan_model* m, int batch, int precision) {
+  if (!m || batch < 0) return 0;
+  return round_up_z(dan_workspace_bytes(m, batch, precision), 256) + host_stage_bytes(m, batch);
+}
+
+int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
+                     const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks, int batch,
+                     float* heads_out_host, void* workspace, size_t workspace_bytes, void* stream) {
+  g_launches = 0;
+  int rc = check_forward_args(m, precision, reads, q_scores, strands, ref, ref_masks, var_masks, batch, heads_out_host);
+  if (rc) return rc;
+  if (batch == 0) return DAN_OK;
+  const size_t core = round_up_z(dan_workspace_bytes(m, batch, precision), 256);
+  if (!workspace || workspace_bytes < core + host_stage_bytes(m, batch)) { dan_set_error("workspace too small for host staging"); return DAN_E_WORKSPACE; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  char* p = static_cast<char*>(workspace) + core;
+  const size_t tile = (size_t)batch * m->P * m->R, vec = (size_t)batch * m->P;
+  auto stage = [&](const uint8_t* src, size_t n) -> uint8_t* {
+    uint8_t* d = reinterpret_cast<uint8_t*>(p);
+    p += round_up_z(n, 256);
+    if (!src) return nullptr;
+    cudaMemcpyAsync(d, src, n, cudaMemcpyHostToDevice, st);
+    return d;
+  };
+  DevInputs in{};
+  in.reads = stage(reads, tile); in.q = stage(q_scores, tile); in.strands = stage(strands, tile);
+  in.ref = stage(ref, vec); in.ref_masks = stage(ref_masks, vec); in.var_masks = stage(var_masks, vec);
+  float* dheads = reinterpret_cast<float*>(p);
+  DAN_CUDA_TRY(cudaGetLastError());
+  if (precision == DAN_PRECISION_BF16) rc = dan_bf16_forward(m, in, batch, dheads, workspace, core, st);
+  else rc = dan_fp32_forward(m, in, batch, dheads, workspace, core, st);
+  if (rc) return rc;
+  DAN_CUDA_TRY(cudaMemcpyAsync(heads_out_host, dheads, (size_t)batch * DAN_NUM_HEAD_OUTPUTS * 4, cudaMemcpyDeviceToHost, st));
+  return DAN_OK;
+}
+
+int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands, const uint8_t* ref,
+               const uint8_t* ref_masks, const uint8_t* var_masks, int batch, float* x0_out, void* stream) {
+  int rc = check_forward_args(m, DAN_PRECISION_FP32, reads, q_scores, strands, ref, ref_masks, var_masks, batch, x0_out);
+  if (rc) return rc;
+  if (batch == 0) return DAN_OK;
+  DevInputs in{reads, q_scores, strands, ref, ref_masks, var_masks};
+  return dan_fp32_encode_reference_order(m, in, batch, x0_out, static_cast<cudaStream_t>(stream));
+}
+
+int dan_debug_fc_input(dan_model* m, int precision, int batch, const void* workspace, float* out, void* stream) {
+  if (!m || !workspace || !out || batch < 1) { dan_set_error("bad argument"); return DAN_E_INVALID; }
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (precision == DAN_PRECISION_BF16) return dan_bf16_debug_fc_input(m, batch, workspace, out, st);
+  return dan_fp32_debug_fc_input(m, batch, workspace, out, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,90 @@
+// dan_internal.h — shared declarations of the DAN B200 library (not part of the public C-ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "../../include/dan_b200.h"
+
+#define DAN_VOCAB 10
+#define DAN_TILE_M 128           // rows (read positions) per GEMM tile, both precisions
+#define DAN_HEAD_PAD 32          // the 27 head outputs are computed as one 32-wide GEMM
+
+static inline int round_up_i(int x, int m) { return (x + m - 1) / m * m; }
+static inline size_t round_up_z(size_t x, size_t m) { return (x + m - 1) / m * m; }
+
+void dan_set_error(const char* fmt, ...);
+void dan_count_launch(int n = 1);
+
+#define DAN_CUDA_TRY(expr)                                                                      \
+  do {                                                                                          \
+    cudaError_t _e = (expr);                                                                    \
+    if (_e != cudaSuccess) {                                                                    \
+      dan_set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      return DAN_E_CUDA;                                                                        \
+    }                                                                                           \
+  } while (0)
+
+// Row geometry of the activation matrices. Every per-read position is one row; reads are laid end to end with
+// `gap` all-zero rows after each read (gap = largest dilation), so a dilated tap is a plain row offset and the
+// zero padding of Conv2d(padding=(0,d)) (reference dl4vc/model.py:214-229) is implicit.
+struct RowGeom {
+  int P;          // positions per read (201)
+  int R;          // reads per candidate (100)
+  int gap;        // zero rows after each read
+  int pitch;      // P + gap
+  __host__ __device__ long rows_of(int cands) const { return (long)cands * R * pitch; }
+};
+
+struct DevInputs {
+  const uint8_t* reads; const uint8_t* q; const uint8_t* strands;
+  const uint8_t* ref; const uint8_t* ref_masks; const uint8_t* var_masks;
+};
+
+struct dan_model {
+  dan_config cfg;
+  int device;
+  int L, C, Cin, CinPad, bott, P, R;
+  RowGeom geom;
+  int pooled, pooledPad;     // pooled feature count ((1|2)*C*P) and its 16-multiple
+  int hwFeat;                // highway features entering the FC
+  int fcIn, fcInPad;         // FC trunk input width
+  int hidden;                // last FC width
+  int pass_candidates;       // candidates per conv-stack pass
+  bool loaded;
+  // ---- fp32 packed weights (device). GEMM weights are stored K-major: W[k][n], n contiguous. ----
+  float* emb; float* pe;
+  float* convW[DAN_MAX_LAYERS];   // [3*CinPad or 3*C][C]   k = tap*Cin_pad + c
+  float* convB[DAN_MAX_LAYERS];
+  float* bnScale[DAN_MAX_LAYERS]; float* bnShift[DAN_MAX_LAYERS];   // eval BatchNorm folded: y*scale+shift
+  float* resW[DAN_MAX_LAYERS];    // [C][C]
+  float* resB[DAN_MAX_LAYERS];
+  float* bottW[DAN_MAX_LAYERS];   // [C][bott]
+  float* bottB[DAN_MAX_LAYERS];
+  float* compW[DAN_MAX_LAYERS];   // [P*bott][bott]         k = p*bott + c
+  float* compB[DAN_MAX_LAYERS];
+  float* postW; float* postB;     // [pooledPad][D]
+  float* fcW[DAN_MAX_FC];         // [KPad][N]
+  float* fcB[DAN_MAX_FC];
+  float* headW; float* headB;     // [hidden][32], [32]
+  // ---- bf16 packed weights for the tcgen05 path (see dan_bf16.cu) ----
+  void* bf16_store;               // opaque Bf16Weights*
+};
+
+// fp32 path (dan_fp32.cu)
+size_t dan_fp32_workspace_bytes(const dan_model* m, int batch);
+int dan_fp32_forward(dan_model* m, const DevInputs& in, int batch, float* heads_out, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+int dan_fp32_encode_reference_order(dan_model* m, const DevInputs& in, int batch, float* x0_out, cudaStream_t st);
+int dan_fp32_debug_fc_input(dan_model* m, int batch, const void* ws, float* out, cudaStream_t st);
+int dan_fp32_pack(dan_model* m, const dan_weights* w, cudaStream_t st);
+void dan_fp32_free(dan_model* m);
+
+// bf16 tcgen05 path (dan_bf16.cu)
+size_t dan_bf16_workspace_bytes(const dan_model* m, int batch);
+int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_out, void* ws, size_t ws_bytes,
+                     cudaStream_t st);
+int dan_bf16_debug_fc_input(dan_model* m, int batch, const void* ws, float* out, cudaStream_t st);
+int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st);
+void dan_bf16_free(dan_model* m);
+int dan_bf16_supported(const dan_model* m);

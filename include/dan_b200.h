@@ -1,0 +1,143 @@
+/* dan_b200.h — C-ABI of the B200-native DAN ("Basic2DNet") forward path.
+ *
+ * The reference has no FFI layer: its boundary for this path is the Python module interface of
+ * dl4vc/model.py (class Basic2DNet, reference dl4vc/model.py:31-961). Each entry point below is what a binding
+ * for that interface has to reach; the citation says which reference lines it replaces. dl4vc_b200/model.py is the
+ * ctypes binding shipped with this repo (INTEGRATION.md shows the three-line overlay for the reference tree).
+ *
+ * Conventions: plain pointers and sizes only (no torch types); every function returns 0 on success or a negative
+ * DAN_E_* code, with a thread-local message available from dan_last_error(); nothing calls exit(). All device
+ * pointers must belong to the CUDA device that was current when the model handle was created. Functions taking a
+ * stream are asynchronous with respect to the host and re-entrant per (model, stream) pair as long as each
+ * concurrent call uses its own workspace.
+ */
+#ifndef DAN_B200_H
+#define DAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DAN_MAX_LAYERS 12
+#define DAN_MAX_FC 4
+#define DAN_NUM_HEAD_OUTPUTS 27 /* xbinary(2) xVT(3) xAF(1) xCov(1) xVB(10) xVR(10): dl4vc/model.py:919-921,953-958 */
+
+enum { DAN_OK = 0, DAN_E_INVALID = -1, DAN_E_UNSUPPORTED = -2, DAN_E_CUDA = -3, DAN_E_WORKSPACE = -4 };
+
+/* arithmetic of the contraction kernels */
+enum {
+  DAN_PRECISION_FP32 = 0, /* CUDA-core FFMA, fp32 storage: logits within 1e-4 relative of the reference */
+  DAN_PRECISION_BF16 = 1  /* tcgen05 tensor cores, bf16 operands, fp32 accumulation in TMEM */
+};
+
+/* Shape of the network = the constructor arguments of Basic2DNet that change arithmetic
+ * (dl4vc/model.py:35-53; PROD values = call_variants.sh:101-147). */
+typedef struct dan_config {
+  int32_t total_conv_layers;            /* model.py:45  */
+  int32_t channels;                     /* init_conv_channels == final_conv_channels, model.py:36 */
+  int32_t embed_dim;                    /* model.py:36 (20) */
+  int32_t use_q_scores;                 /* model.py:38 */
+  int32_t use_strands;                  /* model.py:38 */
+  int32_t use_reads_ref_var_mask;       /* model.py:40 */
+  int32_t dilation[DAN_MAX_LAYERS];     /* per layer, model.py:213-229 */
+  int32_t is_residual[DAN_MAX_LAYERS];  /* model.py:246 */
+  int32_t pool_after[DAN_MAX_LAYERS];   /* 1: read-mean of this layer's output is added to the next layer's input, model.py:734-742,766-772 */
+  int32_t use_batchnorm;                /* model.py:49 */
+  int32_t highway;                      /* append_bottleneck_highway_reads, model.py:43 */
+  int32_t bottleneck;                   /* bottleneck_channels == bottleneck_linear_outputs, model.py:42 */
+  int32_t concat_hw_reads;              /* model.py:43 */
+  int32_t pool_combine_dimension;       /* model.py:51 */
+  int32_t skip_final_maxpool;           /* model.py:51 */
+  int32_t num_fc;                       /* len(layer_sizes), model.py:35 */
+  int32_t fc_sizes[DAN_MAX_FC];
+  int32_t num_reads;                    /* 100, model.py:41 / dataset.py:398 */
+  int32_t read_len;                     /* 201, model.py:41 */
+} dan_config;
+
+/* fp32 parameter tensors in the reference's state_dict layout, DEVICE pointers.
+ * Unused entries (layers beyond total_conv_layers, disabled features) are NULL. */
+typedef struct dan_weights {
+  const float* embeddings;                      /* (10, embed_dim)                 embeddings.weight */
+  const float* pe;                              /* (read_len, embed_dim)           pe[0] */
+  const float* conv_w[DAN_MAX_LAYERS];          /* (C, Cin, 1, 3)                  conv1D_layers.l.weight */
+  const float* conv_b[DAN_MAX_LAYERS];          /* (C)                                                        */
+  const float* bn_w[DAN_MAX_LAYERS];            /* (C) gamma                       bn1D_layers.l.weight */
+  const float* bn_b[DAN_MAX_LAYERS];            /* (C) beta */
+  const float* bn_mean[DAN_MAX_LAYERS];         /* (C) running_mean */
+  const float* bn_var[DAN_MAX_LAYERS];          /* (C) running_var */
+  const float* res_w[DAN_MAX_LAYERS];           /* (C, C, 1, 1) indexed by LAYER (0-based), NULL if not residual */
+  const float* res_b[DAN_MAX_LAYERS];
+  const float* bott_w[DAN_MAX_LAYERS];          /* (bott, C, 1, 1)                 conv1D_bottleneck_layers.l */
+  const float* bott_b[DAN_MAX_LAYERS];
+  const float* comp_w[DAN_MAX_LAYERS];          /* (bott, bott, 1, read_len)       conv1D_compression_layers.l */
+  const float* comp_b[DAN_MAX_LAYERS];
+  const float* post_pool_w;                     /* (pool_combine_dimension, pooled_features) */
+  const float* post_pool_b;
+  const float* fc_w[DAN_MAX_FC];                /* (out, in)                       conv2hidden.{1,4}.weight */
+  const float* fc_b[DAN_MAX_FC];
+  const float* head_w;                          /* (27, hidden) rows in DAN_NUM_HEAD_OUTPUTS order */
+  const float* head_b;                          /* (27) */
+} dan_weights;
+
+typedef struct dan_model dan_model; /* opaque: config + packed device weights */
+
+/* Thread-local text of the last error raised by this library on the calling thread. */
+const char* dan_last_error(void);
+/* Library build identification: "dan_b200 <version> sm_100a". */
+const char* dan_version(void);
+
+/* Replaces Basic2DNet.__init__ (dl4vc/model.py:35-432): validates the configuration and allocates the packed
+ * weight store on the current CUDA device. DAN_E_UNSUPPORTED for shapes the kernels do not cover. */
+int dan_model_create(const dan_config* cfg, dan_model** out);
+int dan_model_destroy(dan_model* m);
+
+/* Replaces load_state_dict / .cuda() (main.py:117,124): folds BatchNorm running statistics into scale/shift,
+ * re-lays every matrix for the kernels (fp32 K-major and bf16 UMMA core-matrix order). Must be called again
+ * whenever parameters change. Asynchronous on `stream`. */
+int dan_model_load_weights(dan_model* m, const dan_weights* w, void* stream);
+
+/* Number of candidates the conv stack processes per internal pass (activations of one pass stay L2-resident). */
+int dan_model_set_pass_candidates(dan_model* m, int candidates);
+
+/* Bytes of device scratch dan_forward needs for a batch of `batch` candidates at `precision`. */
+size_t dan_workspace_bytes(const dan_model* m, int batch, int precision);
+
+/* Replaces Basic2DNet.forward in eval mode (dl4vc/model.py:434-961) for a batch of `batch` candidates.
+ * Inputs are the loader's tensors narrowed to uint8, DEVICE pointers, layout [batch][position][read]
+ * (dl4vc/dataset.py:672-680): reads, q_scores, strands are batch*read_len*num_reads bytes; ref, ref_masks,
+ * var_masks are batch*read_len bytes. q_scores / strands / masks may be NULL when the config does not use them.
+ * heads_out: batch*27 fp32, row = [xbinary(2) xVT(3) sigmoid(xAF) leaky_relu(xCov) xVB(10) xVR(10)]. */
+int dan_forward(dan_model* m, int precision, const uint8_t* reads, const uint8_t* q_scores,
+                const uint8_t* strands, const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks,
+                int batch, float* heads_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Same contract with HOST buffers (pinned for true asynchrony): stages the uint8 inputs to the device on
+ * `stream`, runs dan_forward and copies the batch*27 fp32 results back. Staging memory is taken from the tail of
+ * the workspace (dan_workspace_bytes_host). This is the call the end-to-end benchmark times. */
+size_t dan_workspace_bytes_host(const dan_model* m, int batch, int precision);
+int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const uint8_t* q_scores,
+                     const uint8_t* strands, const uint8_t* ref, const uint8_t* ref_masks,
+                     const uint8_t* var_masks, int batch, float* heads_out_host, void* workspace,
+                     size_t workspace_bytes, void* stream);
+
+/* Test hook for the bit-exact integer/encoding work (dl4vc/model.py:450-627,719): writes the conv-1 input in the
+ * reference's logical order (batch, Cin, num_reads, read_len) fp32, DEVICE pointer. */
+int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
+               const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks, int batch,
+               float* x0_out, void* stream);
+
+/* Test hook: after a dan_forward call on `workspace`, copy the FC input vector (pooled max|mean|relu(highway),
+ * dl4vc/model.py:838-912) of the LAST internal pass to out (rows x fc_in_features fp32, DEVICE pointer).
+ * Returns the number of rows written, or a negative error. */
+int dan_debug_fc_input(dan_model* m, int precision, int batch, const void* workspace, float* out, void* stream);
+
+/* Kernel launches issued by the last dan_forward on this thread (for the benchmark's gpu_launches claim). */
+int dan_last_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DAN_B200_H */

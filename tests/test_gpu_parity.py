@@ -1,0 +1,76 @@
+"""GPU (-m gpu): the CUDA path, called through the C-ABI, against the oracle and the committed reference goldens."""
+import hashlib
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import rel_err, load_golden
+from dl4vc_b200.config import small_config
+from dl4vc_b200.factory import build_model
+from dl4vc_b200.synth import make_pileups
+from dl4vc_b200.weights import synth_state_dict
+from oracle import dan_oracle
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4          # north_star: fp32 logits within 1e-4 relative of the reference
+
+
+def _tensors(arrays):
+    return [torch.from_numpy(np.ascontiguousarray(a)) for a in arrays]
+
+
+def _heads(model, arrays):
+    r, q, s, ref, rm, vm = _tensors(arrays)
+    return model.forward_heads(r, ref, q, s, rm, vm).cpu().numpy()
+
+
+def test_encoder_bit_exact(golden):
+    cfg = golden["cfg"]
+    model = build_model(cfg, synth_state_dict(cfg, seed=golden["seed"]), precision="fp32")
+    r, q, s, ref, rm, vm = _tensors(golden["arrays"])
+    x0 = model.encode(r, ref, q, s, rm, vm).cpu().numpy()
+    digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(x0).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(digest, golden["x0_sha256"]), "conv-1 input differs from the reference bit pattern"
+
+
+def test_fp32_heads_match_reference_goldens(golden):
+    cfg = golden["cfg"]
+    model = build_model(cfg, synth_state_dict(cfg, seed=golden["seed"]), precision="fp32")
+    got = _heads(model, golden["arrays"])
+    assert got.shape == golden["heads"].shape
+    assert rel_err(got, golden["heads"]) < FP32_TOL
+    # the forward() contract: 14-tuple, heads sliced in the reference order (model.py:959-961)
+    r, q, s, ref, rm, vm = _tensors(golden["arrays"])
+    out = model(r.long(), ref.long(), q.long(), s.long(), None, None, None, None, rm.long(), vm.long())
+    assert len(out) == 14 and out[6] == [] and out[7] == [] and out[10] is None
+    assert [tuple(o.shape[1:]) for o in out[:6]] == [(2,), (3,), (1,), (1,), (10,), (10,)]
+    assert np.array_equal(torch.cat(out[:6], dim=1).cpu().numpy(), got)
+
+
+def test_fp32_fc_input_matches_oracle():
+    g = load_golden("prod_smallfc_mixed")
+    cfg = g["cfg"]
+    sd = synth_state_dict(cfg, seed=g["seed"])
+    model = build_model(cfg, sd, precision="fp32")
+    _heads(model, g["arrays"])
+    fc_in = model.debug_fc_input(len(g["reads"])).cpu().numpy()
+    r, q, s, ref, rm, vm = g["arrays"]
+    want = dan_oracle.forward(cfg, sd, r, ref, q, s, rm, vm, keep=True)["fc_in"]
+    assert fc_in.shape == want.shape
+    np.testing.assert_allclose(fc_in, want, rtol=2e-4, atol=2e-5)
+    np.testing.assert_allclose(fc_in[0][::37], g["fc_in_cand0_sample"], rtol=2e-4, atol=2e-5)
+
+
+def test_fp32_batch_split_invariance():
+    """Candidates are independent: any batch split / pass size gives identical rows."""
+    cfg = small_config()
+    sd = synth_state_dict(cfg, seed=9)
+    batch = make_pileups(11, seed=77, coverage="poisson")
+    model = build_model(cfg, sd, precision="fp32")
+    full = _heads(model, batch.arrays())
+    model.set_pass_candidates(3)
+    parts = np.concatenate([_heads(model, batch.slice(lo, hi).arrays()) for lo, hi in ((0, 4), (4, 5), (5, 11))])
+    assert np.array_equal(full, parts)
+    assert _heads(model, batch.slice(0, 0).arrays()).shape == (0, 27)
