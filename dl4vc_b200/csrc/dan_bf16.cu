@@ -1,12 +1,915 @@
-// dan_bf16.cu — tcgen05 (bf16 operands, fp32 TMEM accumulators) implementation of the DAN forward.
+// dan_bf16.cu — tcgen05 implementation of the DAN forward (bf16 operands, fp32 accumulation in TMEM).
+//
+// Activations are stored "chunk-major": for each group of 8 channels (one 16-byte piece per row) the rows of the
+// pass form a dense array:   X[kc][row][8]  (bf16), rows = (candidate, read, position) with `gap` zero rows between
+// reads (RowGeom). A tile of 128 consecutive rows (+ halo) of one channel chunk is therefore ONE contiguous run in
+// HBM, moved by a single bulk async copy, and lands in shared memory exactly in the row-linear UMMA operand layout
+// described in tcgen05_ptx.cuh — the three dilated taps of a conv layer are three start addresses on that tile.
+//
+// Kernels
+//   dan_layer_kernel   one conv layer, fully fused per 128-row tile (dl4vc/model.py:749-778):
+//                      conv(1x3,dil) -> +bias -> ReLU -> BN  [-> 1x1 residual conv + bias + layer input]
+//                      [-> 1x1 bottleneck + bias -> ReLU]; layer weights stay resident in shared memory, two tiles
+//                      are in flight per CTA (TMEM double buffer) so the tensor pipe runs under the epilogue.
+//   stream_gemm_kernel generic split-K GEMM with both operands streamed (highway compression (1x201) conv as one
+//                      K=6432 GEMM over reads, FC trunk, heads).
+#include <cstdio>
+#include <cstring>
+#include <vector>
 #include "dan_kernels_common.cuh"
+#include "tcgen05_ptx.cuh"
 
-int dan_bf16_supported(const dan_model* m) { (void)m; return 0; }
-size_t dan_bf16_workspace_bytes(const dan_model* m, int batch) { (void)m; (void)batch; return 0; }
-int dan_bf16_forward(dan_model*, const DevInputs&, int, float*, void*, size_t, cudaStream_t) {
-  dan_set_error("bf16 path not built");
-  return DAN_E_UNSUPPORTED;
+namespace {
+
+using namespace ptx;
+
+constexpr int kC = 128;               // channels (bf16 path is specialised for the shipped width)
+constexpr int kKC = kC / 8;           // 16-byte pieces per row
+constexpr int kLead = 8;              // zero rows in front of every row matrix (>= largest dilation)
+
+// =====================================================================================================
+// Encoder (bf16, chunk-major output)
+// =====================================================================================================
+__global__ void __launch_bounds__(256) encode_rows_bf16_kernel(EncodeParams p, long cand0, uint4* __restrict__ out, long kstride) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const long cand = cand0 + blockIdx.x;
+  EncodeSmem s = encode_stage(p, cand, smem_raw);
+  const int rows = p.g.R * p.g.pitch;
+  const int kcs = p.CinPad / 8;
+  const long row0 = (long)blockIdx.x * rows;
+  for (int idx = threadIdx.x; idx < rows * kcs; idx += blockDim.x) {
+    const int kc = idx / rows, row = idx - kc * rows;
+    const int r = row / p.g.pitch, pp = row - r * p.g.pitch;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (pp < p.g.P) {
+      float f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = (kc * 8 + j < p.Cin) ? encode_channel(p, s, kc * 8 + j, pp, r) : 0.f;
+      v.x = pack_bf16x2(f[0], f[1]); v.y = pack_bf16x2(f[2], f[3]); v.z = pack_bf16x2(f[4], f[5]); v.w = pack_bf16x2(f[6], f[7]);
+    }
+    out[kc * kstride + kLead + row0 + row] = v;
+  }
 }
-int dan_bf16_debug_fc_input(dan_model*, int, const void*, float*, cudaStream_t) { return DAN_E_UNSUPPORTED; }
-int dan_bf16_pack(dan_model*, const dan_weights*, cudaStream_t) { return DAN_OK; }
-void dan_bf16_free(dan_model*) {}
+
+// =====================================================================================================
+// Fused conv-layer kernel
+// =====================================================================================================
+constexpr int kSlots = 2;
+constexpr int kLayerThreads = 320;    // warps 0-3: epilogue slot 0, 4-7: epilogue slot 1, 8: producer, 9: MMA issuer
+
+struct LayerParams {
+  const uint4* in; long in_kstride;        // chunk-major input, rows per chunk plane
+  uint4* out; long out_kstride;            // chunk-major output (C channels)
+  uint4* tout; long t_reads_stride;        // bottleneck output T[p][c8][read][8]
+  const uint4* wconv; const uint4* wres; const uint4* wbott;   // packed weights (global), smem image
+  long rows_total; int num_tiles;
+  int pitch, P, gap, dil, kc_in, residual, highway, bott;
+  float bias[kC], scale[kC], shift[kC], rbias[kC], bbias[64];
+};
+
+struct LayerSmem {
+  uint64_t w_full, a_full[kSlots], d1_full[kSlots], y_ready[kSlots], d2_full[kSlots], h_ready[kSlots], d3_full[kSlots], slot_free[kSlots];
+  uint32_t tmem_base;
+};
+
+__host__ __device__ inline size_t layer_smem_bytes(int kc_in, int residual, int highway, int bott, int gap) {
+  const size_t slot_rows = 128 + 2 * gap;
+  size_t b = 1024;                                           // barriers + tmem pointer
+  b += (size_t)3 * kc_in * kC * 16;                          // conv weights
+  if (residual) b += (size_t)kKC * kC * 16;
+  if (highway) b += (size_t)kKC * bott * 16;
+  b += (size_t)kSlots * kKC * slot_rows * 16;                // tile slots (hold the halo'd input, then Y / H in place)
+  return b;
+}
+
+__device__ __forceinline__ uint32_t word_of(const uint4& v, int w) { return w == 0 ? v.x : (w == 1 ? v.y : (w == 2 ? v.z : v.w)); }
+
+__global__ void __launch_bounds__(kLayerThreads, 1) dan_layer_kernel(const __grid_constant__ LayerParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  LayerSmem* sm = reinterpret_cast<LayerSmem*>(smem);
+  const int slot_rows = 128 + 2 * p.gap;
+  uint8_t* w_conv = smem + 1024;
+  uint8_t* w_res = w_conv + (size_t)3 * p.kc_in * kC * 16;
+  uint8_t* w_bott = w_res + (p.residual ? (size_t)kKC * kC * 16 : 0);
+  uint8_t* slots = w_bott + (p.highway ? (size_t)kKC * p.bott * 16 : 0);
+  const size_t slot_bytes = (size_t)kKC * slot_rows * 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    mbar_init(&sm->w_full, 1);
+    for (int s = 0; s < kSlots; ++s) {
+      mbar_init(&sm->a_full[s], 1); mbar_init(&sm->d1_full[s], 1); mbar_init(&sm->d2_full[s], 1); mbar_init(&sm->d3_full[s], 1);
+      mbar_init(&sm->y_ready[s], 128); mbar_init(&sm->h_ready[s], 128); mbar_init(&sm->slot_free[s], 128);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 9) tmem_alloc<512>(&sm->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm->tmem_base;
+  const int iters = (p.num_tiles + kSlots * gridDim.x - 1) / (kSlots * gridDim.x);
+
+  if (warp == 8) {
+    // ===================== producer: weights once, then one halo'd input tile per (iteration, slot) ==========
+    if (lane == 0) {
+      const uint32_t conv_bytes = 3u * p.kc_in * kC * 16, res_bytes = p.residual ? kKC * kC * 16 : 0, bott_bytes = p.highway ? kKC * p.bott * 16 : 0;
+      mbar_expect_tx(&sm->w_full, conv_bytes + res_bytes + bott_bytes);
+      for (uint32_t off = 0; off < conv_bytes; off += 16384) bulk_g2s(w_conv + off, reinterpret_cast<const uint8_t*>(p.wconv) + off, min(16384u, conv_bytes - off), &sm->w_full);
+      for (uint32_t off = 0; off < res_bytes; off += 16384) bulk_g2s(w_res + off, reinterpret_cast<const uint8_t*>(p.wres) + off, min(16384u, res_bytes - off), &sm->w_full);
+      if (bott_bytes) bulk_g2s(w_bott, p.wbott, bott_bytes, &sm->w_full);
+      for (int it = 0; it < iters; ++it) {
+        for (int s = 0; s < kSlots; ++s) {
+          const int tile = (it * gridDim.x + blockIdx.x) * kSlots + s;
+          if (tile >= p.num_tiles) continue;
+          mbar_wait(&sm->slot_free[s], (it & 1) ^ 1);
+          const uint32_t bytes = (uint32_t)slot_rows * 16;
+          mbar_expect_tx(&sm->a_full[s], bytes * p.kc_in);
+          const uint4* src = p.in + kLead + (long)tile * 128 - p.gap;
+          uint8_t* dst = slots + s * slot_bytes;
+          for (int kc = 0; kc < p.kc_in; ++kc) bulk_g2s(dst + (size_t)kc * bytes, src + kc * p.in_kstride, bytes, &sm->a_full[s]);
+        }
+      }
+    }
+  } else if (warp == 9) {
+    // ===================== MMA issuer (one thread) ==============================================================
+    if (lane == 0) {
+      const uint32_t idesc_c = make_idesc_bf16(128, kC);
+      const uint32_t idesc_b = make_idesc_bf16(128, p.bott > 0 ? p.bott : 16);
+      const uint32_t lbo_a = (uint32_t)slot_rows * 16;
+      mbar_wait(&sm->w_full, 0);
+      for (int it = 0; it < iters; ++it) {
+        const uint32_t ph = it & 1;
+        // conv taps: D1 = sum_t A[rows + (t-1)*dil] * Wt^T
+        for (int s = 0; s < kSlots; ++s) {
+          const int tile = (it * gridDim.x + blockIdx.x) * kSlots + s;
+          if (tile >= p.num_tiles) continue;
+          mbar_wait(&sm->a_full[s], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(slots + s * slot_bytes);
+          const uint32_t d1 = tmem_base + s * 256;
+          uint32_t acc = 0;
+          for (int t = 0; t < 3; ++t) {
+            const uint32_t a_t = a0 + (uint32_t)(p.gap + (t - 1) * p.dil) * 16;
+            const uint32_t b_t = smem_u32(w_conv) + (uint32_t)t * p.kc_in * (kC * 16);
+            for (int k2 = 0; k2 < p.kc_in; k2 += 2) {
+              umma_bf16(d1, make_smem_desc(a_t + k2 * lbo_a, lbo_a, 128), make_smem_desc(b_t + k2 * (kC * 16), kC * 16, 128), idesc_c, acc);
+              acc = 1;
+            }
+          }
+          umma_commit(&sm->d1_full[s]);
+        }
+        if (p.residual) {
+          for (int s = 0; s < kSlots; ++s) {
+            const int tile = (it * gridDim.x + blockIdx.x) * kSlots + s;
+            if (tile >= p.num_tiles) continue;
+            mbar_wait(&sm->y_ready[s], ph);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(slots + s * slot_bytes) + (uint32_t)p.gap * 16;
+            const uint32_t d2 = tmem_base + s * 256;
+            for (int k2 = 0; k2 < kKC; k2 += 2)
+              umma_bf16(d2, make_smem_desc(a0 + k2 * lbo_a, lbo_a, 128), make_smem_desc(smem_u32(w_res) + k2 * (kC * 16), kC * 16, 128), idesc_c, k2 > 0);
+            umma_commit(&sm->d2_full[s]);
+          }
+        }
+        if (p.highway) {
+          for (int s = 0; s < kSlots; ++s) {
+            const int tile = (it * gridDim.x + blockIdx.x) * kSlots + s;
+            if (tile >= p.num_tiles) continue;
+            mbar_wait(&sm->h_ready[s], ph);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(slots + s * slot_bytes) + (uint32_t)p.gap * 16;
+            const uint32_t d3 = tmem_base + s * 256 + 128;
+            for (int k2 = 0; k2 < kKC; k2 += 2)
+              umma_bf16(d3, make_smem_desc(a0 + k2 * lbo_a, lbo_a, 128), make_smem_desc(smem_u32(w_bott) + k2 * (p.bott * 16), p.bott * 16, 128), idesc_b, k2 > 0);
+            umma_commit(&sm->d3_full[s]);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue warps: thread = one row of the tile =========================================
+    const int s = warp >> 2, q = warp & 3;
+    const int i = q * 32 + lane;
+    const uint32_t d_base = tmem_base + s * 256 + ((uint32_t)(q * 32) << 16);
+    uint4* slot_row = reinterpret_cast<uint4*>(slots + s * slot_bytes) + (p.gap + i);
+    const bool to_smem = p.residual || p.highway;
+    for (int it = 0; it < iters; ++it) {
+      const int tile = (it * gridDim.x + blockIdx.x) * kSlots + s;
+      if (tile >= p.num_tiles) break;
+      const uint32_t ph = it & 1;
+      const long m = (long)tile * 128 + i;
+      const int pp = (int)(m % p.pitch);
+      const bool valid = (m < p.rows_total) && (pp < p.P);
+      uint4* out_row = p.out + kLead + m;
+
+      mbar_wait(&sm->d1_full[s], ph);
+      tc_fence_after();
+      uint4 resid[kKC];
+      if (p.residual) {
+#pragma unroll
+        for (int kc = 0; kc < kKC; ++kc) resid[kc] = slot_row[kc * slot_rows];   // layer input of this row (before the in-place overwrite)
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        uint32_t r[32];
+        tmem_ld32(d_base + c * 32, r);
+        tmem_ld_wait();
+        float f[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float v = __uint_as_float(r[j]) + p.bias[c * 32 + j];
+          v = fmaxf(v, 0.f);                                             // ReLU, then BatchNorm (model.py:749-751)
+          v = fmaf(v, p.scale[c * 32 + j], p.shift[c * 32 + j]);
+          f[j] = valid ? v : 0.f;
+        }
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;
+          o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]); o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+          o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]); o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+          const int kc = c * 4 + g;
+          if (!p.residual) out_row[kc * p.out_kstride] = o;
+          if (to_smem) slot_row[kc * slot_rows] = o;
+        }
+      }
+      if (to_smem) fence_proxy_async_smem();
+      tc_fence_before();
+      if (p.residual) {
+        mbar_arrive(&sm->y_ready[s]);
+        mbar_wait(&sm->d2_full[s], ph);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t r[32];
+          tmem_ld32(d_base + c * 32, r);
+          tmem_ld_wait();
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const uint32_t rw = word_of(resid[c * 4 + (j >> 3)], (j & 7) >> 1);
+            const float rv = (j & 1) ? bf16_hi(rw) : bf16_lo(rw);
+            const float v = __uint_as_float(r[j]) + p.rbias[c * 32 + j] + rv;    // 1x1 conv + bias + layer input (model.py:760-761)
+            f[j] = valid ? v : 0.f;
+          }
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            uint4 o;
+            o.x = pack_bf16x2(f[g * 8 + 0], f[g * 8 + 1]); o.y = pack_bf16x2(f[g * 8 + 2], f[g * 8 + 3]);
+            o.z = pack_bf16x2(f[g * 8 + 4], f[g * 8 + 5]); o.w = pack_bf16x2(f[g * 8 + 6], f[g * 8 + 7]);
+            const int kc = c * 4 + g;
+            out_row[kc * p.out_kstride] = o;
+            if (p.highway) slot_row[kc * slot_rows] = o;
+          }
+        }
+        if (p.highway) fence_proxy_async_smem();
+        tc_fence_before();
+      }
+      if (p.highway) {
+        mbar_arrive(&sm->h_ready[s]);
+        mbar_wait(&sm->d3_full[s], ph);
+        tc_fence_after();
+        const long read = m / p.pitch;
+        for (int c = 0; c < p.bott / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(d_base + 128 + c * 32, r);
+          tmem_ld_wait();
+          if (valid) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+              float f[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(r[g * 8 + j]) + p.bbias[c * 32 + g * 8 + j], 0.f);   // model.py:774
+              uint4 o;
+              o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
+              p.tout[((long)pp * (p.bott / 8) + c * 4 + g) * p.t_reads_stride + read] = o;
+            }
+          }
+        }
+        tc_fence_before();
+      }
+      mbar_arrive(&sm->slot_free[s]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 9) tmem_dealloc<512>(tmem_base);
+}
+
+// =====================================================================================================
+// Streaming split-K GEMM:  out[M][N] (+)= A[M][K] * B[N][K]^T, both operands chunk-major (16-byte pieces)
+// =====================================================================================================
+constexpr int kGemmThreads = 192;     // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
+constexpr int kStageKC = 8;           // 8 pieces = 64 K elements per stage
+
+struct GemmParams {
+  const uint4* A; long a_kstride;
+  const uint4* B; long b_kstride;
+  int M, N, KC;                       // KC = K/8 (even)
+  int m_tiles, n_tiles, splits;
+  float* out; int ldo;
+};
+
+template <int BN>
+__host__ __device__ constexpr int gemm_stages() { return BN == 128 ? 6 : 8; }
+template <int BN>
+__host__ __device__ constexpr size_t gemm_smem_bytes() { return 1024 + (size_t)gemm_stages<BN>() * kStageKC * (128 + BN) * 16; }
+
+template <int BN>
+__global__ void __launch_bounds__(kGemmThreads, 1) stream_gemm_kernel(const __grid_constant__ GemmParams p) {
+  constexpr int NS = gemm_stages<BN>();
+  constexpr uint32_t kABytes = kStageKC * 128 * 16, kBBytes = kStageKC * BN * 16;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty = full + NS;
+  uint64_t* done = empty + NS;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
+  uint8_t* stage_base = smem + 1024;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  int w = blockIdx.x;
+  const int m_tile = w % p.m_tiles; w /= p.m_tiles;
+  const int n_tile = w % p.n_tiles; w /= p.n_tiles;
+  const int split = w;
+  const int total_stages = (p.KC + kStageKC - 1) / kStageKC;
+  const int per = (total_stages + p.splits - 1) / p.splits;
+  const int st_begin = split * per, st_end = min(total_stages, st_begin + per);
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    mbar_init(done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 1) tmem_alloc<BN < 32 ? 32 : BN>(tmem_ptr);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (st_begin < st_end) {
+    if (warp == 0) {
+      if (lane == 0) {
+        for (int st = st_begin; st < st_end; ++st) {
+          const int i = (st - st_begin) % NS, round = (st - st_begin) / NS;
+          mbar_wait(&empty[i], (round & 1) ^ 1);
+          const int kc0 = st * kStageKC, nkc = min(kStageKC, p.KC - kc0);
+          mbar_expect_tx(&full[i], (uint32_t)nkc * (128 + BN) * 16);
+          uint8_t* a_dst = stage_base + (size_t)i * (kABytes + kBBytes);
+          uint8_t* b_dst = a_dst + kABytes;
+          for (int k = 0; k < nkc; ++k) {
+            bulk_g2s(a_dst + k * 128 * 16, p.A + (long)(kc0 + k) * p.a_kstride + (long)m_tile * 128, 128 * 16, &full[i]);
+            bulk_g2s(b_dst + k * BN * 16, p.B + (long)(kc0 + k) * p.b_kstride + (long)n_tile * BN, BN * 16, &full[i]);
+          }
+        }
+      }
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc_bf16(128, BN);
+        uint32_t acc = 0;
+        for (int st = st_begin; st < st_end; ++st) {
+          const int i = (st - st_begin) % NS, round = (st - st_begin) / NS;
+          mbar_wait(&full[i], round & 1);
+          tc_fence_after();
+          const int kc0 = st * kStageKC, nkc = min(kStageKC, p.KC - kc0);
+          const uint32_t a0 = smem_u32(stage_base + (size_t)i * (kABytes + kBBytes)), b0 = a0 + kABytes;
+          for (int k2 = 0; k2 < nkc; k2 += 2) {
+            umma_bf16(tmem_base, make_smem_desc(a0 + k2 * (128 * 16), 128 * 16, 128), make_smem_desc(b0 + k2 * (BN * 16), BN * 16, 128), idesc, acc);
+            acc = 1;
+          }
+          umma_commit(&empty[i]);
+        }
+        umma_commit(done);
+      }
+    } else {
+      const int q = warp & 3;
+      const int row = m_tile * 128 + q * 32 + lane;
+      mbar_wait(done, 0);
+      tc_fence_after();
+      float* orow = p.out + (long)row * p.ldo + (long)n_tile * BN;
+#pragma unroll
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
+        tmem_ld_wait();
+        if (row < p.M) {
+          if (p.splits > 1) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) atomicAdd(orow + c * 32 + j, __uint_as_float(r[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 1) tmem_dealloc<BN < 32 ? 32 : BN>(tmem_base);
+}
+
+// =====================================================================================================
+// Elementwise / reduction helpers on chunk-major bf16
+// =====================================================================================================
+__device__ __forceinline__ void unpack8(const uint4& v, float (&f)[8]) {
+  f[0] = bf16_lo(v.x); f[1] = bf16_hi(v.x); f[2] = bf16_lo(v.y); f[3] = bf16_hi(v.y);
+  f[4] = bf16_lo(v.z); f[5] = bf16_hi(v.z); f[6] = bf16_lo(v.w); f[7] = bf16_hi(v.w);
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+}
+
+// pool[cand][p][c] = mean over reads (fp32)   (model.py:772)
+__global__ void pool_mean_bf16_kernel(const uint4* __restrict__ h, long kstride, float* __restrict__ pool, RowGeom g) {
+  const int cand = blockIdx.y, kc = blockIdx.z;
+  const int pp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pp >= g.P) return;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const uint4* src = h + kc * kstride + kLead + (long)cand * g.R * g.pitch + pp;
+  for (int r = 0; r < g.R; ++r) {
+    float f[8];
+    unpack8(__ldg(src + (long)r * g.pitch), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s[j] += f[j];
+  }
+  float* dst = pool + ((long)cand * g.P + pp) * kC + kc * 8;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) dst[j] = s[j] / (float)g.R;
+}
+
+// out = bf16(h + pool) on data rows, 0 on gap rows   (model.py:742)
+__global__ void add_pool_bf16_kernel(const uint4* __restrict__ h, const float* __restrict__ pool, uint4* __restrict__ out,
+                                     long kstride, long rows, RowGeom g) {
+  const long total = rows * kKC;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int kc = (int)(i / rows); const long row = i - (long)kc * rows;
+    const int pp = (int)(row % g.pitch); const long cand = row / ((long)g.R * g.pitch);
+    uint4 v = h[kc * kstride + kLead + row];
+    if (pp < g.P) {
+      float f[8];
+      unpack8(v, f);
+      const float4* a = reinterpret_cast<const float4*>(pool + (cand * g.P + pp) * kC + kc * 8);
+      const float4 a0 = a[0], a1 = a[1];
+      f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w; f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
+      v = pack8(f);
+    }
+    out[kc * kstride + kLead + row] = v;
+  }
+}
+
+// final max ‖ mean over reads -> FC input pieces (bf16 feature order: max p*C+c | mean P*C+p*C+c)
+__global__ void pool_final_bf16_kernel(const uint4* __restrict__ h, long kstride, uint4* __restrict__ fcin, long fc_kstride,
+                                       int cand0, RowGeom g, int skip_max) {
+  const int cand = blockIdx.y, kc = blockIdx.z;
+  const int pp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pp >= g.P) return;
+  float s[8] = {0, 0, 0, 0, 0, 0, 0, 0}, mx[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
+  const uint4* src = h + kc * kstride + kLead + (long)cand * g.R * g.pitch + pp;
+  for (int r = 0; r < g.R; ++r) {
+    float f[8];
+    unpack8(__ldg(src + (long)r * g.pitch), f);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { s[j] += f[j]; mx[j] = fmaxf(mx[j], f[j]); }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s[j] /= (float)g.R;
+  const long col = cand0 + cand;
+  if (skip_max) {
+    fcin[((long)pp * kKC + kc) * fc_kstride + col] = pack8(s);
+  } else {
+    fcin[((long)pp * kKC + kc) * fc_kstride + col] = pack8(mx);
+    fcin[((long)(g.P + pp) * kKC + kc) * fc_kstride + col] = pack8(s);
+  }
+}
+
+// highway: hw fp32 partial [l][read][bott] + bias -> relu -> FC input pieces   (model.py:853-859)
+__global__ void highway_finish_bf16_kernel(const float* __restrict__ hw, long layer_stride, const float* const* __restrict__ bias_by_layer,
+                                           int L, int bott, int R, int concat, uint4* __restrict__ fcin, long fc_kstride,
+                                           long base_kc, int cand0, int cands) {
+  const int o8n = bott / 8;
+  const long total = (long)cands * (concat ? L : 1) * R * o8n;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int o8 = (int)(i % o8n); long t = i / o8n;
+    const int r = (int)(t % R); t /= R;
+    const int l = concat ? (int)(t % L) : 0; const long cand = concat ? t / L : t;
+    float f[8];
+    if (concat) {
+      const float* src = hw + l * layer_stride + (cand * R + r) * bott + o8 * 8;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(src[j] + bias_by_layer[l][o8 * 8 + j], 0.f);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = 0.f;
+      for (int k = 0; k < L; ++k) {
+        const float* src = hw + k * layer_stride + (cand * R + r) * bott + o8 * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] += src[j] + bias_by_layer[k][o8 * 8 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j] / (float)L, 0.f);
+    }
+    fcin[(base_kc + ((long)l * R + r) * o8n + o8) * fc_kstride + cand0 + cand] = pack8(f);
+  }
+}
+
+// FC finish: partial fp32 [M][N] + bias -> relu -> bf16 pieces [N/8][kstride]
+__global__ void fc_finish_bf16_kernel(const float* __restrict__ part, int M, int N, const float* __restrict__ bias,
+                                      uint4* __restrict__ out, long kstride) {
+  const long total = (long)M * (N / 8);
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int m = (int)(i % M); const int kc = (int)(i / M);
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = fmaxf(part[(long)m * N + kc * 8 + j] + bias[kc * 8 + j], 0.f);
+    out[kc * kstride + m] = pack8(f);
+  }
+}
+__global__ void heads_finish_kernel(const float* __restrict__ part, int M, const float* __restrict__ bias, float* __restrict__ out) {
+  const long total = (long)M * DAN_NUM_HEAD_OUTPUTS;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int n = (int)(i % DAN_NUM_HEAD_OUTPUTS); const long m = i / DAN_NUM_HEAD_OUTPUTS;
+    float v = part[m * DAN_HEAD_PAD + n] + bias[n];
+    if (n == 5) v = 1.f / (1.f + expf(-v));
+    else if (n == 6) v = v >= 0.f ? v : 0.01f * v;
+    out[i] = v;
+  }
+}
+
+// =====================================================================================================
+// Weight packing (fp32 state_dict tensors -> bf16 operand images)
+// =====================================================================================================
+__device__ __forceinline__ void store_bf16(uint4* base, long piece, int j, float v) {
+  reinterpret_cast<__nv_bfloat16*>(base + piece)[j] = __float2bfloat16_rn(v);
+}
+// conv (Cout, Cin, 1, 3) -> [tap][kc][n][8]
+__global__ void pack_conv_bf16_kernel(const float* __restrict__ w, uint4* __restrict__ out, int Cin, int kc_in) {
+  const long total = (long)3 * kc_in * kC * 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7); long t = i >> 3;
+    const int n = (int)(t % kC); t /= kC;
+    const int kc = (int)(t % kc_in); const int tap = (int)(t / kc_in);
+    const int c = kc * 8 + j;
+    store_bf16(out, ((long)tap * kc_in + kc) * kC + n, j, c < Cin ? w[((long)n * Cin + c) * 3 + tap] : 0.f);
+  }
+}
+// linear-like (N, K) fp32 with optional source-column map -> [kc][Npad][8]
+__global__ void pack_linear_bf16_kernel(const float* __restrict__ w, uint4* __restrict__ out, int N, int Npad, int K, int Kpad,
+                                        int mode, int P, int C, int R, int bott, int L, int pooled, int skip_max) {
+  // mode 0: identity columns. mode 1: FC1 feature permutation (see dan_bf16_forward). mode 2: compression (O, Cb, 1, P): k = p*bott + c
+  const long total = (long)(Kpad / 8) * Npad * 8;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int j = (int)(i & 7); long t = i >> 3;
+    const int n = (int)(t % Npad); const long kc = t / Npad;
+    const long k = kc * 8 + j;
+    float v = 0.f;
+    if (n < N && k < K) {
+      long src = k;
+      if (mode == 1) {
+        if (k < pooled) {
+          const long blk = k / ((long)P * C);            // 0 = max block (or mean when skip_max), 1 = mean block
+          const long rem = k - blk * P * C;
+          const int pp = (int)(rem / C), c = (int)(rem % C);
+          src = (blk * C + c) * (long)P + pp;
+        } else {
+          const long h = k - pooled;
+          const int o = (int)(h % bott); const long lr = h / bott;
+          const int r = (int)(lr % R); const int l = (int)(lr / R);
+          src = pooled + (long)l * bott * R + (long)o * R + r;
+        }
+      } else if (mode == 2) {
+        const int c = (int)(k % bott), pp = (int)(k / bott);
+        src = (long)c * P + pp;                           // within row n: (c, p)
+      }
+      v = w[(long)n * K + src];
+    }
+    store_bf16(out, kc * Npad + n, j, v);
+  }
+}
+
+struct Bf16Weights {
+  uint4* wconv[DAN_MAX_LAYERS]; uint4* wres[DAN_MAX_LAYERS]; uint4* wbott[DAN_MAX_LAYERS]; uint4* wcomp[DAN_MAX_LAYERS];
+  uint4* fcw[DAN_MAX_FC]; uint4* headw;
+  const float** comp_bias_ptrs;       // device array of L pointers
+  // host copies of the per-channel epilogue constants (kernel parameters -> constant bank)
+  float bias[DAN_MAX_LAYERS][kC], scale[DAN_MAX_LAYERS][kC], shift[DAN_MAX_LAYERS][kC], rbias[DAN_MAX_LAYERS][kC], bbias[DAN_MAX_LAYERS][64];
+  int num_sms;
+};
+
+inline int grid_for(long total, int block = 256) {
+  long g = (total + block - 1) / block;
+  return (int)(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g));
+}
+
+// workspace carve-up ---------------------------------------------------------------------------------------
+struct Bf16Plan {
+  int S, Bc, BcPad;
+  long rows, rowsPad, kstride;       // per pass; kstride = rows per chunk plane
+  long readsPad;
+  long hw_layer_stride;
+  int fcKC;                          // FC input pieces
+  size_t off_zero_begin, off_x0, off_h[3], off_zero_end, off_t, off_pool, off_hw, off_fcin, off_fcx[DAN_MAX_FC], off_part, total;
+  int maxN;
+};
+
+Bf16Plan make_plan(const dan_model* m, int batch) {
+  Bf16Plan pl{};
+  pl.S = m->pass_candidates < batch ? m->pass_candidates : (batch > 0 ? batch : 1);
+  pl.Bc = batch < 1024 ? (batch > 0 ? batch : 1) : 1024;
+  pl.BcPad = round_up_i(pl.Bc, 128);
+  pl.rows = m->geom.rows_of(pl.S);
+  pl.rowsPad = (pl.rows + 127) / 128 * 128;
+  pl.kstride = kLead + pl.rowsPad + 8;
+  pl.readsPad = ((long)pl.S * m->R + 127) / 128 * 128;
+  pl.fcKC = m->fcInPad / 8;
+  size_t off = 0;
+  auto take = [&](size_t bytes) { size_t o = off; off += round_up_z(bytes, 1024); return o; };
+  pl.off_zero_begin = off;
+  pl.off_x0 = take((size_t)(m->CinPad / 8) * pl.kstride * 16);
+  for (int i = 0; i < 3; ++i) pl.off_h[i] = take((size_t)kKC * pl.kstride * 16);
+  pl.off_zero_end = off;
+  const int bott = m->bott > 0 ? m->bott : 32;
+  pl.off_t = take((size_t)m->P * (bott / 8) * pl.readsPad * 16);
+  pl.off_pool = take((size_t)pl.S * m->P * kC * 4);
+  pl.hw_layer_stride = pl.readsPad * bott;
+  pl.off_hw = take((size_t)m->L * pl.hw_layer_stride * 4);
+  pl.off_fcin = take((size_t)pl.fcKC * pl.BcPad * 16);
+  pl.maxN = DAN_HEAD_PAD;
+  for (int i = 0; i < m->cfg.num_fc; ++i) {
+    pl.off_fcx[i] = take((size_t)(m->cfg.fc_sizes[i] / 8) * pl.BcPad * 16);
+    if (m->cfg.fc_sizes[i] > pl.maxN) pl.maxN = m->cfg.fc_sizes[i];
+  }
+  pl.off_part = take((size_t)pl.BcPad * pl.maxN * 4);
+  pl.total = off;
+  return pl;
+}
+
+template <int BN>
+int launch_gemm_bn(const GemmParams& g, cudaStream_t st) {
+  static thread_local bool attr = false;
+  if (!attr) {
+    DAN_CUDA_TRY(cudaFuncSetAttribute(stream_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<BN>()));
+    attr = true;
+  }
+  stream_gemm_kernel<BN><<<g.m_tiles * g.n_tiles * g.splits, kGemmThreads, gemm_smem_bytes<BN>(), st>>>(g);
+  dan_count_launch();
+  DAN_CUDA_TRY(cudaGetLastError());
+  return DAN_OK;
+}
+
+// out (fp32, zeroed here when split) = A * B^T
+int run_gemm(const uint4* A, long a_kstride, const uint4* B, long b_kstride, int M, int N, int KC, float* out, int ldo,
+             int num_sms, cudaStream_t st) {
+  GemmParams g{};
+  g.A = A; g.a_kstride = a_kstride; g.B = B; g.b_kstride = b_kstride; g.M = M; g.N = N; g.KC = KC; g.out = out; g.ldo = ldo;
+  const int bn = N >= 128 ? 128 : 32;
+  g.m_tiles = (M + 127) / 128; g.n_tiles = N / bn;
+  const int total_stages = (KC + kStageKC - 1) / kStageKC;
+  int splits = 1;
+  const int base = g.m_tiles * g.n_tiles;
+  if (base < num_sms) splits = (num_sms + base - 1) / base;
+  if (splits > total_stages / 4) splits = total_stages / 4 > 0 ? total_stages / 4 : 1;
+  // avoid empty trailing splits
+  const int per = (total_stages + splits - 1) / splits;
+  splits = (total_stages + per - 1) / per;
+  g.splits = splits;
+  if (splits > 1) DAN_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)M * ldo * 4, st));
+  return bn == 128 ? launch_gemm_bn<128>(g, st) : launch_gemm_bn<32>(g, st);
+}
+
+}  // namespace
+
+// ----------------------------------------------------------------------------------------------------------
+int dan_bf16_supported(const dan_model* m) {
+  if (m->C != kC) return 0;
+  if (m->cfg.pool_combine_dimension != 0) return 0;
+  if (m->cfg.highway && !(m->bott == 32 || m->bott == 64)) return 0;
+  if (m->geom.gap > kLead) return 0;
+  if (m->CinPad % 16) return 0;
+  for (int i = 0; i < m->cfg.num_fc; ++i) if (m->cfg.fc_sizes[i] % 32) return 0;
+  return 1;
+}
+
+size_t dan_bf16_workspace_bytes(const dan_model* m, int batch) {
+  if (!dan_bf16_supported(m)) return 0;
+  return make_plan(m, batch).total;
+}
+
+int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
+  Bf16Weights* bw = static_cast<Bf16Weights*>(m->bf16_store);
+  if (!bw) {
+    bw = new Bf16Weights();
+    memset(bw, 0, sizeof(*bw));
+    m->bf16_store = bw;
+    cudaDeviceGetAttribute(&bw->num_sms, cudaDevAttrMultiProcessorCount, m->device);
+  }
+  const int L = m->L, bott = m->bott, P = m->P, R = m->R;
+  auto alloc = [&](uint4** p, size_t pieces) -> int {
+    if (*p) return DAN_OK;
+    DAN_CUDA_TRY(cudaMalloc(p, pieces * 16));
+    return DAN_OK;
+  };
+  int rc;
+  for (int l = 0; l < L; ++l) {
+    const int cin = l == 0 ? m->Cin : kC, kc_in = (l == 0 ? m->CinPad : kC) / 8;
+    if ((rc = alloc(&bw->wconv[l], (size_t)3 * kc_in * kC))) return rc;
+    pack_conv_bf16_kernel<<<grid_for((long)3 * kc_in * kC * 8), 256, 0, st>>>(w->conv_w[l], bw->wconv[l], cin, kc_in);
+    if (m->cfg.is_residual[l]) {
+      if ((rc = alloc(&bw->wres[l], (size_t)kKC * kC))) return rc;
+      pack_linear_bf16_kernel<<<grid_for((long)kKC * kC * 8), 256, 0, st>>>(w->res_w[l], bw->wres[l], kC, kC, kC, kC, 0, P, kC, R, bott, L, 0, 0);
+    }
+    if (m->cfg.highway) {
+      if ((rc = alloc(&bw->wbott[l], (size_t)kKC * bott))) return rc;
+      pack_linear_bf16_kernel<<<grid_for((long)kKC * bott * 8), 256, 0, st>>>(w->bott_w[l], bw->wbott[l], bott, bott, kC, kC, 0, P, kC, R, bott, L, 0, 0);
+      const int K = P * bott;
+      if ((rc = alloc(&bw->wcomp[l], (size_t)(K / 8) * bott))) return rc;
+      pack_linear_bf16_kernel<<<grid_for((long)K * bott), 256, 0, st>>>(w->comp_w[l], bw->wcomp[l], bott, bott, K, K, 2, P, kC, R, bott, L, 0, 0);
+    }
+  }
+  int K = m->fcIn, Kpad = m->fcInPad;
+  for (int i = 0; i < m->cfg.num_fc; ++i) {
+    const int N = m->cfg.fc_sizes[i];
+    if ((rc = alloc(&bw->fcw[i], (size_t)(Kpad / 8) * N))) return rc;
+    pack_linear_bf16_kernel<<<grid_for((long)Kpad * N), 256, 0, st>>>(w->fc_w[i], bw->fcw[i], N, N, K, Kpad, i == 0 ? 1 : 0, P, kC, R, bott,
+                                                                      m->cfg.concat_hw_reads ? L : 1, m->pooled, m->cfg.skip_final_maxpool);
+    K = N; Kpad = N;
+  }
+  if ((rc = alloc(&bw->headw, (size_t)(m->hidden / 8) * DAN_HEAD_PAD))) return rc;
+  pack_linear_bf16_kernel<<<grid_for((long)m->hidden * DAN_HEAD_PAD), 256, 0, st>>>(w->head_w, bw->headw, DAN_NUM_HEAD_OUTPUTS, DAN_HEAD_PAD, m->hidden, m->hidden, 0, P, kC, R, bott, L, 0, 0);
+  DAN_CUDA_TRY(cudaGetLastError());
+  // epilogue constants -> host (the fp32 packer already folded BatchNorm on this stream)
+  DAN_CUDA_TRY(cudaStreamSynchronize(st));
+  for (int l = 0; l < L; ++l) {
+    DAN_CUDA_TRY(cudaMemcpy(bw->bias[l], m->convB[l], kC * 4, cudaMemcpyDeviceToHost));
+    if (m->cfg.use_batchnorm) {
+      DAN_CUDA_TRY(cudaMemcpy(bw->scale[l], m->bnScale[l], kC * 4, cudaMemcpyDeviceToHost));
+      DAN_CUDA_TRY(cudaMemcpy(bw->shift[l], m->bnShift[l], kC * 4, cudaMemcpyDeviceToHost));
+    } else {
+      for (int c = 0; c < kC; ++c) { bw->scale[l][c] = 1.f; bw->shift[l][c] = 0.f; }
+    }
+    if (m->cfg.is_residual[l]) DAN_CUDA_TRY(cudaMemcpy(bw->rbias[l], m->resB[l], kC * 4, cudaMemcpyDeviceToHost));
+    if (m->cfg.highway) DAN_CUDA_TRY(cudaMemcpy(bw->bbias[l], m->bottB[l], bott * 4, cudaMemcpyDeviceToHost));
+  }
+  if (m->cfg.highway) {
+    if (!bw->comp_bias_ptrs) DAN_CUDA_TRY(cudaMalloc(&bw->comp_bias_ptrs, sizeof(float*) * DAN_MAX_LAYERS));
+    DAN_CUDA_TRY(cudaMemcpy(bw->comp_bias_ptrs, m->compB, sizeof(float*) * L, cudaMemcpyHostToDevice));
+  }
+  return DAN_OK;
+}
+
+void dan_bf16_free(dan_model* m) {
+  Bf16Weights* bw = static_cast<Bf16Weights*>(m->bf16_store);
+  if (!bw) return;
+  for (int l = 0; l < DAN_MAX_LAYERS; ++l) { cudaFree(bw->wconv[l]); cudaFree(bw->wres[l]); cudaFree(bw->wbott[l]); cudaFree(bw->wcomp[l]); }
+  for (int i = 0; i < DAN_MAX_FC; ++i) cudaFree(bw->fcw[i]);
+  cudaFree(bw->headw);
+  cudaFree(bw->comp_bias_ptrs);
+  delete bw;
+  m->bf16_store = nullptr;
+}
+
+int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+  Bf16Weights* bw = static_cast<Bf16Weights*>(m->bf16_store);
+  if (!bw) { dan_set_error("bf16 weights not packed"); return DAN_E_INVALID; }
+  const Bf16Plan pl = make_plan(m, batch);
+  if (ws_bytes < pl.total) { dan_set_error("workspace too small: %zu < %zu", ws_bytes, pl.total); return DAN_E_WORKSPACE; }
+  char* base = static_cast<char*>(ws);
+  const RowGeom g = m->geom;
+  const int L = m->L, bott = m->bott, P = m->P, R = m->R;
+  uint4* X0 = reinterpret_cast<uint4*>(base + pl.off_x0);
+  uint4* H[3]; for (int i = 0; i < 3; ++i) H[i] = reinterpret_cast<uint4*>(base + pl.off_h[i]);
+  uint4* T = reinterpret_cast<uint4*>(base + pl.off_t);
+  float* POOL = reinterpret_cast<float*>(base + pl.off_pool);
+  float* HW = reinterpret_cast<float*>(base + pl.off_hw);
+  uint4* FCIN = reinterpret_cast<uint4*>(base + pl.off_fcin);
+  float* PART = reinterpret_cast<float*>(base + pl.off_part);
+  int rc;
+
+  static thread_local bool attr_set = false;
+  const size_t enc_smem = encode_smem_bytes(P, R, m->cfg.embed_dim);
+  if (!attr_set) {
+    DAN_CUDA_TRY(cudaFuncSetAttribute(encode_rows_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem));
+    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  // halo rows (and the rows past the last tile) must read as zero: clear the row matrices once per call
+  DAN_CUDA_TRY(cudaMemsetAsync(base + pl.off_zero_begin, 0, pl.off_zero_end - pl.off_zero_begin, st));
+
+  EncodeParams ep{};
+  ep.in = in; ep.emb = m->emb; ep.pe = m->pe; ep.D = m->cfg.embed_dim; ep.Cin = m->Cin; ep.CinPad = m->CinPad;
+  ep.use_q = m->cfg.use_q_scores; ep.use_s = m->cfg.use_strands; ep.use_m = m->cfg.use_reads_ref_var_mask; ep.g = g;
+
+  for (int c0 = 0; c0 < batch; c0 += pl.Bc) {
+    const int nb = batch - c0 < pl.Bc ? batch - c0 : pl.Bc;
+    if (m->fcInPad != m->fcIn) DAN_CUDA_TRY(cudaMemsetAsync(FCIN, 0, (size_t)pl.fcKC * pl.BcPad * 16, st));
+    for (int s0 = 0; s0 < nb; s0 += pl.S) {
+      const int ns = nb - s0 < pl.S ? nb - s0 : pl.S;
+      const long rows = g.rows_of(ns);
+      const int num_tiles = (int)((rows + 127) / 128);
+      encode_rows_bf16_kernel<<<ns, 256, enc_smem, st>>>(ep, (long)c0 + s0, X0, pl.kstride);
+      dan_count_launch();
+      DAN_CUDA_TRY(cudaGetLastError());
+      const uint4* cur = X0;
+      int hsel = 0;
+      for (int l = 0; l < L; ++l) {
+        const uint4* conv_in = cur;
+        if (l > 0 && m->cfg.pool_after[l - 1]) {
+          uint4* hp = H[(hsel + 2) % 3];
+          add_pool_bf16_kernel<<<grid_for(rows * kKC), 256, 0, st>>>(cur, POOL, hp, pl.kstride, rows, g);
+          dan_count_launch();
+          DAN_CUDA_TRY(cudaGetLastError());
+          conv_in = hp;
+        }
+        uint4* next = H[(hsel + 1) % 3];
+        if (m->cfg.is_residual[l] && conv_in != cur) { dan_set_error("bf16 path: residual layer directly after a pool-add layer is not supported"); return DAN_E_UNSUPPORTED; }
+        LayerParams lp{};
+        lp.in = conv_in; lp.in_kstride = pl.kstride; lp.out = next; lp.out_kstride = pl.kstride;
+        lp.tout = T; lp.t_reads_stride = pl.readsPad;
+        lp.wconv = bw->wconv[l]; lp.wres = bw->wres[l]; lp.wbott = bw->wbott[l];
+        lp.rows_total = rows; lp.num_tiles = num_tiles; lp.pitch = g.pitch; lp.P = P; lp.gap = g.gap; lp.dil = m->cfg.dilation[l];
+        lp.kc_in = (l == 0 ? m->CinPad : kC) / 8; lp.residual = m->cfg.is_residual[l]; lp.highway = m->cfg.highway; lp.bott = bott;
+        memcpy(lp.bias, bw->bias[l], sizeof(lp.bias)); memcpy(lp.scale, bw->scale[l], sizeof(lp.scale)); memcpy(lp.shift, bw->shift[l], sizeof(lp.shift));
+        memcpy(lp.rbias, bw->rbias[l], sizeof(lp.rbias)); memcpy(lp.bbias, bw->bbias[l], sizeof(lp.bbias));
+        const size_t smem = layer_smem_bytes(lp.kc_in, lp.residual, lp.highway, bott, g.gap);
+        int grid = (num_tiles + kSlots - 1) / kSlots;
+        if (grid > bw->num_sms) grid = bw->num_sms;
+        dan_layer_kernel<<<grid, kLayerThreads, smem, st>>>(lp);
+        dan_count_launch();
+        DAN_CUDA_TRY(cudaGetLastError());
+        if (m->cfg.pool_after[l]) {
+          pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(next, pl.kstride, POOL, g);
+          dan_count_launch();
+          DAN_CUDA_TRY(cudaGetLastError());
+        }
+        if (m->cfg.highway) {
+          rc = run_gemm(T, pl.readsPad, bw->wcomp[l], bott, ns * R, bott, P * bott / 8, HW + (long)l * pl.hw_layer_stride, bott, bw->num_sms, st);
+          if (rc) return rc;
+        }
+        cur = next; hsel = (hsel + 1) % 3;
+      }
+      pool_final_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(cur, pl.kstride, FCIN, pl.BcPad, s0, g, m->cfg.skip_final_maxpool);
+      dan_count_launch();
+      DAN_CUDA_TRY(cudaGetLastError());
+      if (m->cfg.highway) {
+        const int Lh = m->cfg.concat_hw_reads ? L : 1;
+        highway_finish_bf16_kernel<<<grid_for((long)ns * Lh * R * (bott / 8)), 256, 0, st>>>(
+            HW, pl.hw_layer_stride, bw->comp_bias_ptrs, L, bott, R, m->cfg.concat_hw_reads, FCIN, pl.BcPad, m->pooled / 8, s0, ns);
+        dan_count_launch();
+        DAN_CUDA_TRY(cudaGetLastError());
+      }
+    }
+    // ---- FC trunk + heads (model.py:917-958) ----
+    const uint4* x = FCIN; int KC = pl.fcKC;
+    for (int i = 0; i < m->cfg.num_fc; ++i) {
+      const int N = m->cfg.fc_sizes[i];
+      rc = run_gemm(x, pl.BcPad, bw->fcw[i], N, nb, N, KC, PART, N, bw->num_sms, st);
+      if (rc) return rc;
+      uint4* y = reinterpret_cast<uint4*>(base + pl.off_fcx[i]);
+      fc_finish_bf16_kernel<<<grid_for((long)nb * (N / 8)), 256, 0, st>>>(PART, nb, N, m->fcB[i], y, pl.BcPad);
+      dan_count_launch();
+      DAN_CUDA_TRY(cudaGetLastError());
+      x = y; KC = N / 8;
+    }
+    rc = run_gemm(x, pl.BcPad, bw->headw, DAN_HEAD_PAD, nb, DAN_HEAD_PAD, KC, PART, DAN_HEAD_PAD, bw->num_sms, st);
+    if (rc) return rc;
+    heads_finish_kernel<<<grid_for((long)nb * DAN_NUM_HEAD_OUTPUTS), 256, 0, st>>>(PART, nb, m->headB, heads_out + (long)c0 * DAN_NUM_HEAD_OUTPUTS);
+    dan_count_launch();
+    DAN_CUDA_TRY(cudaGetLastError());
+  }
+  return DAN_OK;
+}
+
+// FC input in the REFERENCE feature order (fp32), undoing the bf16 path's feature permutation (test hook)
+namespace {
+__global__ void fcin_to_reference_order_kernel(const uint4* __restrict__ fcin, long kstride, int rows, float* __restrict__ out,
+                                               int fcIn, int pooled, int P, int C, int R, int bott) {
+  const long total = (long)rows * fcIn;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int f = (int)(i % fcIn); const long m = i / fcIn;
+    long k;
+    if (f < pooled) {
+      const int blk = f / (C * P), rem = f % (C * P);
+      const int c = rem / P, pp = rem % P;
+      k = (long)blk * P * C + (long)pp * C + c;
+    } else {
+      const int h = f - pooled;
+      const int l = h / (bott * R), rem = h % (bott * R);
+      const int o = rem / R, r = rem % R;
+      k = pooled + ((long)l * R + r) * bott + o;
+    }
+    const __nv_bfloat16* piece = reinterpret_cast<const __nv_bfloat16*>(fcin + (k / 8) * kstride + m);
+    out[i] = __bfloat162float(piece[k % 8]);
+  }
+}
+}  // namespace
+
+int dan_bf16_debug_fc_input(dan_model* m, int batch, const void* ws, float* out, cudaStream_t st) {
+  const Bf16Plan pl = make_plan(m, batch);
+  const int nb = batch % pl.Bc == 0 ? pl.Bc : batch % pl.Bc;
+  const uint4* FCIN = reinterpret_cast<const uint4*>(static_cast<const char*>(ws) + pl.off_fcin);
+  fcin_to_reference_order_kernel<<<grid_for((long)nb * m->fcIn), 256, 0, st>>>(FCIN, pl.BcPad, nb, out, m->fcIn, m->pooled, m->P, kC, m->R, m->bott > 0 ? m->bott : 1);
+  DAN_CUDA_TRY(cudaGetLastError());
+  return nb;
+}
