@@ -61,6 +61,7 @@ struct LayerParams {
   const uint4* in; long in_kstride;        // chunk-major input, rows per chunk plane
   uint4* out; long out_kstride;            // chunk-major output (C channels)
   uint4* tout; long t_reads_stride;        // bottleneck output T[p][c8][read][8]
+  const uint4* resid;                      // residual source when it differs from the conv input (pool-add layers), else null
   const uint4* wconv; const uint4* wres; const uint4* wbott;   // packed weights (global), smem image
   long rows_total; int num_tiles;
   int pitch, P, gap, dil, kc_in, residual, highway, bott;
@@ -208,7 +209,8 @@ __global__ void __launch_bounds__(kLayerThreads, 1) dan_layer_kernel(const __gri
       uint4 resid[kKC];
       if (p.residual) {
 #pragma unroll
-        for (int kc = 0; kc < kKC; ++kc) resid[kc] = slot_row[kc * slot_rows];   // layer input of this row (before the in-place overwrite)
+        for (int kc = 0; kc < kKC; ++kc)   // layer input of this row (taken before the in-place overwrite; model.py:732)
+          resid[kc] = p.resid ? __ldg(p.resid + kLead + m + kc * p.in_kstride) : slot_row[kc * slot_rows];
       }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
@@ -823,10 +825,10 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           conv_in = hp;
         }
         uint4* next = H[(hsel + 1) % 3];
-        if (m->cfg.is_residual[l] && conv_in != cur) { dan_set_error("bf16 path: residual layer directly after a pool-add layer is not supported"); return DAN_E_UNSUPPORTED; }
         LayerParams lp{};
         lp.in = conv_in; lp.in_kstride = pl.kstride; lp.out = next; lp.out_kstride = pl.kstride;
         lp.tout = T; lp.t_reads_stride = pl.readsPad;
+        lp.resid = (m->cfg.is_residual[l] && conv_in != cur) ? cur : nullptr;   // residual excludes the pool term (model.py:732 vs :742)
         lp.wconv = bw->wconv[l]; lp.wres = bw->wres[l]; lp.wbott = bw->wbott[l];
         lp.rows_total = rows; lp.num_tiles = num_tiles; lp.pitch = g.pitch; lp.P = P; lp.gap = g.gap; lp.dil = m->cfg.dilation[l];
         lp.kc_in = (l == 0 ? m->CinPad : kC) / 8; lp.residual = m->cfg.is_residual[l]; lp.highway = m->cfg.highway; lp.bott = bott;
