@@ -655,7 +655,7 @@ int launch_gemm_bn(const GemmParams& g, cudaStream_t st) {
     DAN_CUDA_TRY(cudaFuncSetAttribute(stream_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<BN>()));
     attr = true;
   }
-  stream_gemm_kernel<BN><<<g.m_tiles * g.n_tiles * g.splits, kGemmThreads, gemm_smem_bytes<BN>(), st>>>(g);
+  { DanProfScope ps(DAN_PROF_GEMM, st); stream_gemm_kernel<BN><<<g.m_tiles * g.n_tiles * g.splits, kGemmThreads, gemm_smem_bytes<BN>(), st>>>(g); }
   dan_count_launch();
   DAN_CUDA_TRY(cudaGetLastError());
   return DAN_OK;
@@ -810,7 +810,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
       const int ns = nb - s0 < pl.S ? nb - s0 : pl.S;
       const long rows = g.rows_of(ns);
       const int num_tiles = (int)((rows + 127) / 128);
-      encode_rows_bf16_kernel<<<ns, 256, enc_smem, st>>>(ep, (long)c0 + s0, X0, pl.kstride);
+      { DanProfScope ps(DAN_PROF_ENCODE, st); encode_rows_bf16_kernel<<<ns, 256, enc_smem, st>>>(ep, (long)c0 + s0, X0, pl.kstride); }
       dan_count_launch();
       DAN_CUDA_TRY(cudaGetLastError());
       const uint4* cur = X0;
@@ -819,7 +819,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
         const uint4* conv_in = cur;
         if (l > 0 && m->cfg.pool_after[l - 1]) {
           uint4* hp = H[(hsel + 2) % 3];
-          add_pool_bf16_kernel<<<grid_for(rows * kKC), 256, 0, st>>>(cur, POOL, hp, pl.kstride, rows, g);
+          { DanProfScope ps(DAN_PROF_POOL, st); add_pool_bf16_kernel<<<grid_for(rows * kKC), 256, 0, st>>>(cur, POOL, hp, pl.kstride, rows, g); }
           dan_count_launch();
           DAN_CUDA_TRY(cudaGetLastError());
           conv_in = hp;
@@ -837,11 +837,11 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
         const size_t smem = layer_smem_bytes(lp.kc_in, lp.residual, lp.highway, bott, g.gap);
         int grid = (num_tiles + kSlots - 1) / kSlots;
         if (grid > bw->num_sms) grid = bw->num_sms;
-        dan_layer_kernel<<<grid, kLayerThreads, smem, st>>>(lp);
+        { DanProfScope ps(DAN_PROF_CONV_STACK, st); dan_layer_kernel<<<grid, kLayerThreads, smem, st>>>(lp); }
         dan_count_launch();
         DAN_CUDA_TRY(cudaGetLastError());
         if (m->cfg.pool_after[l]) {
-          pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(next, pl.kstride, POOL, g);
+          { DanProfScope ps(DAN_PROF_POOL, st); pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(next, pl.kstride, POOL, g); }
           dan_count_launch();
           DAN_CUDA_TRY(cudaGetLastError());
         }
@@ -851,13 +851,13 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
         }
         cur = next; hsel = (hsel + 1) % 3;
       }
-      pool_final_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(cur, pl.kstride, FCIN, pl.BcPad, s0, g, m->cfg.skip_final_maxpool);
+      { DanProfScope ps(DAN_PROF_POOL, st); pool_final_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(cur, pl.kstride, FCIN, pl.BcPad, s0, g, m->cfg.skip_final_maxpool); }
       dan_count_launch();
       DAN_CUDA_TRY(cudaGetLastError());
       if (m->cfg.highway) {
         const int Lh = m->cfg.concat_hw_reads ? L : 1;
-        highway_finish_bf16_kernel<<<grid_for((long)ns * Lh * R * (bott / 8)), 256, 0, st>>>(
-            HW, pl.hw_layer_stride, bw->comp_bias_ptrs, L, bott, R, m->cfg.concat_hw_reads, FCIN, pl.BcPad, m->pooled / 8, s0, ns);
+        { DanProfScope ps(DAN_PROF_POOL, st); highway_finish_bf16_kernel<<<grid_for((long)ns * Lh * R * (bott / 8)), 256, 0, st>>>(
+            HW, pl.hw_layer_stride, bw->comp_bias_ptrs, L, bott, R, m->cfg.concat_hw_reads, FCIN, pl.BcPad, m->pooled / 8, s0, ns); }
         dan_count_launch();
         DAN_CUDA_TRY(cudaGetLastError());
       }
@@ -869,14 +869,14 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
       rc = run_gemm(x, pl.BcPad, bw->fcw[i], N, nb, N, KC, PART, N, bw->num_sms, st);
       if (rc) return rc;
       uint4* y = reinterpret_cast<uint4*>(base + pl.off_fcx[i]);
-      fc_finish_bf16_kernel<<<grid_for((long)nb * (N / 8)), 256, 0, st>>>(PART, nb, N, m->fcB[i], y, pl.BcPad);
+      { DanProfScope ps(DAN_PROF_POOL, st); fc_finish_bf16_kernel<<<grid_for((long)nb * (N / 8)), 256, 0, st>>>(PART, nb, N, m->fcB[i], y, pl.BcPad); }
       dan_count_launch();
       DAN_CUDA_TRY(cudaGetLastError());
       x = y; KC = N / 8;
     }
     rc = run_gemm(x, pl.BcPad, bw->headw, DAN_HEAD_PAD, nb, DAN_HEAD_PAD, KC, PART, DAN_HEAD_PAD, bw->num_sms, st);
     if (rc) return rc;
-    heads_finish_kernel<<<grid_for((long)nb * DAN_NUM_HEAD_OUTPUTS), 256, 0, st>>>(PART, nb, m->headB, heads_out + (long)c0 * DAN_NUM_HEAD_OUTPUTS);
+    { DanProfScope ps(DAN_PROF_POOL, st); heads_finish_kernel<<<grid_for((long)nb * DAN_NUM_HEAD_OUTPUTS), 256, 0, st>>>(PART, nb, m->headB, heads_out + (long)c0 * DAN_NUM_HEAD_OUTPUTS); }
     dan_count_launch();
     DAN_CUDA_TRY(cudaGetLastError());
   }

@@ -5,10 +5,40 @@
 #include <new>
 #include "dan_internal.h"
 
+#include <vector>
+#include <mutex>
+
 namespace {
 thread_local char g_error[512] = "";
 thread_local int g_launches = 0;
+
+// ---- optional per-kernel-class timing (CUDA events on the launching stream; off by default) ----
+struct ProfSpan { cudaEvent_t a, b; int cls; };
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfSpan> g_prof_spans;
+std::vector<cudaEvent_t> g_prof_pool;
+cudaEvent_t prof_event() {
+  if (!g_prof_pool.empty()) { cudaEvent_t e = g_prof_pool.back(); g_prof_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
 }  // namespace
+
+void dan_prof_begin(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfSpan s{prof_event(), prof_event(), cls};
+  cudaEventRecord(s.a, st);
+  g_prof_spans.push_back(s);
+}
+void dan_prof_end(int cls, cudaStream_t st) {
+  if (!g_prof_on) return;
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (size_t i = g_prof_spans.size(); i-- > 0;)
+    if (g_prof_spans[i].cls == cls) { cudaEventRecord(g_prof_spans[i].b, st); break; }
+}
 
 void dan_set_error(const char* fmt, ...) {
   va_list ap;
@@ -23,6 +53,32 @@ extern "C" {
 const char* dan_last_error(void) { return g_error; }
 const char* dan_version(void) { return "dan_b200 0.1 sm_100a"; }
 int dan_last_launch_count(void) { return g_launches; }
+
+int dan_profile_enable(int on) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = on != 0;
+  for (auto& s : g_prof_spans) { g_prof_pool.push_back(s.a); g_prof_pool.push_back(s.b); }
+  g_prof_spans.clear();
+  return DAN_OK;
+}
+
+int dan_profile_read(double* ms_by_class, int* launches_by_class, int num_classes) {
+  if (!ms_by_class || !launches_by_class || num_classes < 1) { dan_set_error("bad argument"); return DAN_E_INVALID; }
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (int i = 0; i < num_classes; ++i) { ms_by_class[i] = 0.0; launches_by_class[i] = 0; }
+  for (auto& s : g_prof_spans) {
+    if (cudaEventSynchronize(s.b) != cudaSuccess) { dan_set_error("profile event not recorded"); return DAN_E_CUDA; }
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) != cudaSuccess) { dan_set_error("cudaEventElapsedTime failed"); return DAN_E_CUDA; }
+    if (s.cls >= 0 && s.cls < num_classes) { ms_by_class[s.cls] += ms; launches_by_class[s.cls] += 1; }
+  }
+  return (int)g_prof_spans.size();
+}
+
+const char* dan_profile_class_name(int cls) {
+  static const char* names[DAN_PROF_NUM_CLASSES] = {"conv_stack", "gemm", "encode", "pool_elementwise"};
+  return (cls >= 0 && cls < DAN_PROF_NUM_CLASSES) ? names[cls] : "";
+}
 
 int dan_model_create(const dan_config* cfg, dan_model** out) {
   if (!cfg || !out) { dan_set_error("null argument"); return DAN_E_INVALID; }

@@ -15,6 +15,14 @@ static inline size_t round_up_z(size_t x, size_t m) { return (x + m - 1) / m * m
 
 void dan_set_error(const char* fmt, ...);
 void dan_count_launch(int n = 1);
+// kernel-class timing spans (no-ops unless dan_profile_enable(1)); classes: DAN_PROF_*
+void dan_prof_begin(int cls, cudaStream_t st);
+void dan_prof_end(int cls, cudaStream_t st);
+struct DanProfScope {
+  int cls; cudaStream_t st;
+  DanProfScope(int c, cudaStream_t s) : cls(c), st(s) { dan_prof_begin(cls, st); }
+  ~DanProfScope() { dan_prof_end(cls, st); }
+};
 
 #define DAN_CUDA_TRY(expr)                                                                      \
   do {                                                                                          \

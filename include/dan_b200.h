@@ -137,6 +137,15 @@ int dan_debug_fc_input(dan_model* m, int precision, int batch, const void* works
 /* Kernel launches issued by the last dan_forward on this thread (for the benchmark's gpu_launches claim). */
 int dan_last_launch_count(void);
 
+/* Measurement hook (bench.py roofline): when enabled, every kernel launch of dan_forward is bracketed by CUDA
+ * events on the launching stream, grouped in DAN_PROF_* classes. dan_profile_enable(1) also clears earlier
+ * spans. dan_profile_read waits for the recorded events and returns the number of spans; ms_by_class /
+ * launches_by_class receive the summed device time and launch count per class. */
+enum { DAN_PROF_CONV_STACK = 0, DAN_PROF_GEMM = 1, DAN_PROF_ENCODE = 2, DAN_PROF_POOL = 3, DAN_PROF_NUM_CLASSES = 4 };
+int dan_profile_enable(int on);
+int dan_profile_read(double* ms_by_class, int* launches_by_class, int num_classes);
+const char* dan_profile_class_name(int cls);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,3 +46,14 @@ def test_match_masks_bit_exact(golden):
                     np.broadcast_to(nzR[:, None, :], (reads.shape[0], cfg.num_reads, cfg.read_len))], axis=1)
     want = golden["x0_mask_channels"][:, k - 2 * cfg.embed_dim:].astype(np.float32)
     assert np.array_equal(got.astype(np.float32), want)
+
+
+def test_torch_cpu_port_matches_reference_goldens(golden):
+    """bench.py's CPU baseline (oracle/dan_torch_cpu.py: the reference's own torch op sequence) gives the reference's results."""
+    from oracle import dan_torch_cpu
+
+    cfg = golden["cfg"]
+    sd = synth_state_dict(cfg, seed=golden["seed"])
+    reads, q, s, ref, rm, vm = golden["arrays"]
+    heads = dan_torch_cpu.forward(cfg, sd, reads, ref, q, s, rm, vm).numpy()
+    assert rel_err(heads, golden["heads"]) < 5e-6
