@@ -14,6 +14,7 @@
 //   stream_gemm_kernel generic split-K GEMM with both operands streamed (highway compression (1x201) conv as one
 //                      K=6432 GEMM over reads, FC trunk, heads).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "dan_kernels_common.cuh"
@@ -49,6 +50,92 @@ __global__ void __launch_bounds__(256) encode_rows_bf16_kernel(EncodeParams p, l
     }
     out[kc * kstride + kLead + row0 + row] = v;
   }
+}
+
+// ---- fast encoder for the shipped channel set (embed_dim 20, q-scores, strands, ref/var masks: 45 -> 48 channels) ----
+// Two launches: (1) per-read agreement bits with the ref / var proposal (integer compare over all positions,
+// model.py:592-593,607-608); (2) one CTA per (16-position chunk, candidate): the three byte tiles of the chunk are
+// contiguous in the loader's [position][read] layout (dataset.py:672-680), the embedding + positional sums are built
+// once per (position, token) in shared memory as bf16, and every 16-byte output piece is one shared-memory read.
+constexpr int kEncPB = 16;
+__global__ void __launch_bounds__(128) agree_bits_kernel(DevInputs in, long cand0, int P, int R, uint8_t* __restrict__ agree) {
+  const long cand = cand0 + blockIdx.x;
+  __shared__ uint8_t rm[512], vm[512];
+  for (int i = threadIdx.x; i < P; i += blockDim.x) { rm[i] = in.ref_masks[cand * P + i]; vm[i] = in.var_masks[cand * P + i]; }
+  __syncthreads();
+  for (int r = threadIdx.x; r < R; r += blockDim.x) {
+    bool okR = true, okV = true;
+    const uint8_t* rd = in.reads + cand * P * R + r;
+    for (int pp = 0; pp < P; ++pp) {
+      const uint8_t a = rm[pp], b = vm[pp];
+      if (a | b) {
+        const uint8_t t = __ldg(rd + (long)pp * R);
+        okR = okR && (a == 0 || t == a);
+        okV = okV && (b == 0 || t == b);
+      }
+    }
+    agree[((long)blockIdx.x * 2 + 0) * R + r] = okR;
+    agree[((long)blockIdx.x * 2 + 1) * R + r] = okV;
+  }
+}
+
+__global__ void __launch_bounds__(256) encode_prod_bf16_kernel(DevInputs in, const float* __restrict__ emb, const float* __restrict__ pe,
+                                                               const uint8_t* __restrict__ agree, long cand0, RowGeom g,
+                                                               uint4* __restrict__ out, long kstride) {
+  constexpr int D = 20, PB = kEncPB;
+  const int P = g.P, R = g.R;
+  const int cl = blockIdx.y;
+  const long cand = cand0 + cl;
+  const int p0 = blockIdx.x * PB;
+  const int np = min(PB, P - p0);
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint4* tabR = reinterpret_cast<uint4*>(smem_raw);                 // [PB][10][3] pieces: ch 0-7 | 8-15 | 16-19 + ref 0-3
+  uint4* tabF = tabR + PB * DAN_VOCAB * 3;                           // [PB][2] pieces: ref 4-11 | ref 12-19
+  uint8_t* rd = reinterpret_cast<uint8_t*>(tabF + PB * 2);           // [PB][R]
+  uint8_t* qq = rd + PB * R;
+  uint8_t* ss = qq + PB * R;
+  uint8_t* fl = ss + PB * R;                                         // [PB] ref token, [PB] nzR, [PB] nzV
+  uint8_t* ag = fl + 3 * PB;                                         // [2][R]
+  const long toff = cand * P * R + (long)p0 * R;
+  for (int i = threadIdx.x; i < np * R; i += blockDim.x) { rd[i] = __ldg(in.reads + toff + i); qq[i] = __ldg(in.q + toff + i); ss[i] = __ldg(in.strands + toff + i); }
+  for (int i = threadIdx.x; i < np; i += blockDim.x) {
+    fl[i] = __ldg(in.ref + cand * P + p0 + i);
+    fl[PB + i] = __ldg(in.ref_masks + cand * P + p0 + i) != 0;
+    fl[2 * PB + i] = __ldg(in.var_masks + cand * P + p0 + i) != 0;
+  }
+  for (int i = threadIdx.x; i < 2 * R; i += blockDim.x) ag[i] = agree[(long)cl * 2 * R + i];
+  __syncthreads();
+  __nv_bfloat16* tR = reinterpret_cast<__nv_bfloat16*>(tabR);
+  for (int i = threadIdx.x; i < np * DAN_VOCAB * 24; i += blockDim.x) {
+    const int c = i % 24, tok = (i / 24) % DAN_VOCAB, pl = i / (24 * DAN_VOCAB);
+    const int pp = p0 + pl;
+    const float v = c < D ? emb[tok * D + c] + pe[pp * D + c] : emb[fl[pl] * D + (c - D)] + pe[pp * D + (c - D)];
+    tR[i] = __float2bfloat16_rn(v);
+  }
+  __nv_bfloat16* tF = reinterpret_cast<__nv_bfloat16*>(tabF);
+  for (int i = threadIdx.x; i < np * 16; i += blockDim.x) {
+    const int c = 4 + (i & 15), pl = i >> 4;
+    tF[i] = __float2bfloat16_rn(emb[fl[pl] * D + c] + pe[(p0 + pl) * D + c]);
+  }
+  __syncthreads();
+  const long row_base = kLead + (long)cl * R * g.pitch + p0;
+  const int items = 6 * R * PB;
+  for (int i = threadIdx.x; i < items; i += blockDim.x) {
+    const int pl = i % PB, r = (i / PB) % R, kc = i / (PB * R);
+    if (pl >= np) continue;
+    uint4 v;
+    if (kc < 3) v = tabR[(pl * DAN_VOCAB + rd[pl * R + r]) * 3 + kc];
+    else if (kc < 5) v = tabF[pl * 2 + (kc - 3)];
+    else {
+      const float m0 = (fl[PB + pl] && ag[r]) ? 1.f : 0.f, m1 = (fl[2 * PB + pl] && ag[R + r]) ? 1.f : 0.f, m2 = fl[PB + pl] ? 1.f : 0.f;
+      v.x = pack_bf16x2((float)qq[pl * R + r] * 0.01f, (float)ss[pl * R + r] * 0.5f);   // model.py:24,16
+      v.y = pack_bf16x2(m0, m1); v.z = pack_bf16x2(m2, 0.f); v.w = 0u;                 // var_length from the REF mask (model.py:579,584)
+    }
+    out[kc * kstride + row_base + (long)r * g.pitch + pl] = v;
+  }
+}
+__host__ __device__ inline size_t encode_prod_smem_bytes(int R) {
+  return (size_t)kEncPB * DAN_VOCAB * 3 * 16 + kEncPB * 2 * 16 + 3 * kEncPB * R + 3 * kEncPB + 2 * R + 16;
 }
 
 // =====================================================================================================
@@ -411,6 +498,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) stream_gemm_kernel(const __gr
   if (warp == 1) tmem_dealloc<BN < 32 ? 32 : BN>(tmem_base);
 }
 
+}  // namespace
+#include "dan_stack.cuh"
+namespace {
+
 // =====================================================================================================
 // Elementwise / reduction helpers on chunk-major bf16
 // =====================================================================================================
@@ -595,6 +686,8 @@ struct Bf16Weights {
   uint4* wconv[DAN_MAX_LAYERS]; uint4* wres[DAN_MAX_LAYERS]; uint4* wbott[DAN_MAX_LAYERS]; uint4* wcomp[DAN_MAX_LAYERS];
   uint4* fcw[DAN_MAX_FC]; uint4* headw;
   const float** comp_bias_ptrs;       // device array of L pointers
+  uint8_t* wstream[DAN_MAX_LAYERS];   // conv | residual | bottleneck operand images of a layer, contiguous (dan_stack.cuh)
+  float* chan_dev;                    // [L][4][128] conv bias, BN scale, BN shift, residual bias (device)
   // host copies of the per-channel epilogue constants (kernel parameters -> constant bank)
   float bias[DAN_MAX_LAYERS][kC], scale[DAN_MAX_LAYERS][kC], shift[DAN_MAX_LAYERS][kC], rbias[DAN_MAX_LAYERS][kC], bbias[DAN_MAX_LAYERS][64];
   int num_sms;
@@ -611,8 +704,9 @@ struct Bf16Plan {
   long rows, rowsPad, kstride;       // per pass; kstride = rows per chunk plane
   long readsPad;
   long hw_layer_stride;
+  long t_layer_pieces;               // uint4 pieces of one layer's T matrix
   int fcKC;                          // FC input pieces
-  size_t off_zero_begin, off_x0, off_h[3], off_zero_end, off_t, off_pool, off_hw, off_fcin, off_fcx[DAN_MAX_FC], off_part, total;
+  size_t off_zero_begin, off_x0, off_h[3], off_zero_end, off_t, off_pool, off_agree, off_hw, off_fcin, off_fcx[DAN_MAX_FC], off_part, total;
   int maxN;
 };
 
@@ -633,8 +727,10 @@ Bf16Plan make_plan(const dan_model* m, int batch) {
   for (int i = 0; i < 3; ++i) pl.off_h[i] = take((size_t)kKC * pl.kstride * 16);
   pl.off_zero_end = off;
   const int bott = m->bott > 0 ? m->bott : 32;
-  pl.off_t = take((size_t)m->P * (bott / 8) * pl.readsPad * 16);
+  pl.t_layer_pieces = (long)m->P * (bott / 8) * pl.readsPad;
+  pl.off_t = take((size_t)m->L * pl.t_layer_pieces * 16);
   pl.off_pool = take((size_t)pl.S * m->P * kC * 4);
+  pl.off_agree = take((size_t)pl.S * 2 * m->R);
   pl.hw_layer_stride = pl.readsPad * bott;
   pl.off_hw = take((size_t)m->L * pl.hw_layer_stride * 4);
   pl.off_fcin = take((size_t)pl.fcKC * pl.BcPad * 16);
@@ -716,14 +812,18 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
   int rc;
   for (int l = 0; l < L; ++l) {
     const int cin = l == 0 ? m->Cin : kC, kc_in = (l == 0 ? m->CinPad : kC) / 8;
-    if ((rc = alloc(&bw->wconv[l], (size_t)3 * kc_in * kC))) return rc;
+    if (!bw->wstream[l]) {
+      const size_t conv_b = (size_t)3 * kc_in * kC * 16, res_b = m->cfg.is_residual[l] ? (size_t)kKC * kC * 16 : 0, bott_b = m->cfg.highway ? (size_t)kKC * bott * 16 : 0;
+      DAN_CUDA_TRY(cudaMalloc(&bw->wstream[l], conv_b + res_b + bott_b + 16));
+      bw->wconv[l] = reinterpret_cast<uint4*>(bw->wstream[l]);
+      if (res_b) bw->wres[l] = reinterpret_cast<uint4*>(bw->wstream[l] + conv_b);
+      if (bott_b) bw->wbott[l] = reinterpret_cast<uint4*>(bw->wstream[l] + conv_b + res_b);
+    }
     pack_conv_bf16_kernel<<<grid_for((long)3 * kc_in * kC * 8), 256, 0, st>>>(w->conv_w[l], bw->wconv[l], cin, kc_in);
     if (m->cfg.is_residual[l]) {
-      if ((rc = alloc(&bw->wres[l], (size_t)kKC * kC))) return rc;
       pack_linear_bf16_kernel<<<grid_for((long)kKC * kC * 8), 256, 0, st>>>(w->res_w[l], bw->wres[l], kC, kC, kC, kC, 0, P, kC, R, bott, L, 0, 0);
     }
     if (m->cfg.highway) {
-      if ((rc = alloc(&bw->wbott[l], (size_t)kKC * bott))) return rc;
       pack_linear_bf16_kernel<<<grid_for((long)kKC * bott * 8), 256, 0, st>>>(w->bott_w[l], bw->wbott[l], bott, bott, kC, kC, 0, P, kC, R, bott, L, 0, 0);
       const int K = P * bott;
       if ((rc = alloc(&bw->wcomp[l], (size_t)(K / 8) * bott))) return rc;
@@ -754,6 +854,14 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
     if (m->cfg.is_residual[l]) DAN_CUDA_TRY(cudaMemcpy(bw->rbias[l], m->resB[l], kC * 4, cudaMemcpyDeviceToHost));
     if (m->cfg.highway) DAN_CUDA_TRY(cudaMemcpy(bw->bbias[l], m->bottB[l], bott * 4, cudaMemcpyDeviceToHost));
   }
+  if (!bw->chan_dev) DAN_CUDA_TRY(cudaMalloc(&bw->chan_dev, sizeof(float) * DAN_MAX_LAYERS * 4 * kC));
+  for (int l = 0; l < L; ++l) {
+    float* d = bw->chan_dev + (size_t)l * 4 * kC;
+    DAN_CUDA_TRY(cudaMemcpy(d, bw->bias[l], kC * 4, cudaMemcpyHostToDevice));
+    DAN_CUDA_TRY(cudaMemcpy(d + kC, bw->scale[l], kC * 4, cudaMemcpyHostToDevice));
+    DAN_CUDA_TRY(cudaMemcpy(d + 2 * kC, bw->shift[l], kC * 4, cudaMemcpyHostToDevice));
+    DAN_CUDA_TRY(cudaMemcpy(d + 3 * kC, bw->rbias[l], kC * 4, cudaMemcpyHostToDevice));
+  }
   if (m->cfg.highway) {
     if (!bw->comp_bias_ptrs) DAN_CUDA_TRY(cudaMalloc(&bw->comp_bias_ptrs, sizeof(float*) * DAN_MAX_LAYERS));
     DAN_CUDA_TRY(cudaMemcpy(bw->comp_bias_ptrs, m->compB, sizeof(float*) * L, cudaMemcpyHostToDevice));
@@ -764,7 +872,8 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
 void dan_bf16_free(dan_model* m) {
   Bf16Weights* bw = static_cast<Bf16Weights*>(m->bf16_store);
   if (!bw) return;
-  for (int l = 0; l < DAN_MAX_LAYERS; ++l) { cudaFree(bw->wconv[l]); cudaFree(bw->wres[l]); cudaFree(bw->wbott[l]); cudaFree(bw->wcomp[l]); }
+  for (int l = 0; l < DAN_MAX_LAYERS; ++l) { cudaFree(bw->wstream[l]); cudaFree(bw->wcomp[l]); }
+  cudaFree(bw->chan_dev);
   for (int i = 0; i < DAN_MAX_FC; ++i) cudaFree(bw->fcw[i]);
   cudaFree(bw->headw);
   cudaFree(bw->comp_bias_ptrs);
@@ -784,6 +893,9 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
   uint4* H[3]; for (int i = 0; i < 3; ++i) H[i] = reinterpret_cast<uint4*>(base + pl.off_h[i]);
   uint4* T = reinterpret_cast<uint4*>(base + pl.off_t);
   float* POOL = reinterpret_cast<float*>(base + pl.off_pool);
+  uint8_t* AGREE = reinterpret_cast<uint8_t*>(base + pl.off_agree);
+  const bool fast_encode = m->cfg.embed_dim == 20 && m->cfg.use_q_scores && m->cfg.use_strands && m->cfg.use_reads_ref_var_mask && m->CinPad == 48 && P <= 512 &&
+                           encode_prod_smem_bytes(R) <= 48 * 1024;
   float* HW = reinterpret_cast<float*>(base + pl.off_hw);
   uint4* FCIN = reinterpret_cast<uint4*>(base + pl.off_fcin);
   float* PART = reinterpret_cast<float*>(base + pl.off_part);
@@ -796,8 +908,17 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
     DAN_CUDA_TRY(cudaFuncSetAttribute(dan_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  // halo rows (and the rows past the last tile) must read as zero: clear the row matrices once per call
-  DAN_CUDA_TRY(cudaMemsetAsync(base + pl.off_zero_begin, 0, pl.off_zero_end - pl.off_zero_begin, st));
+  bool fused = m->P == 201 && m->geom.gap <= kStkLead && (!m->cfg.highway || bott == 32 || bott == 64) && !getenv("DAN_B200_LAYERWISE");
+  for (int l = 1; l < L; ++l)      // a residual layer fed by a pool-add needs the un-pooled input as residual (model.py:732 vs :742)
+    if (m->cfg.is_residual[l] && m->cfg.pool_after[l - 1]) fused = false;
+  static thread_local bool stack_attr_set = false;
+  if (fused && !stack_attr_set) {
+    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
+    stack_attr_set = true;
+  }
+  // layer-wise path: halo rows (and the rows past the last tile) must read as zero: clear the row matrices once per call.
+  // The fused path loads and stores exactly the P data rows of every read and keeps its zero rows in shared memory.
+  if (!fused) DAN_CUDA_TRY(cudaMemsetAsync(base + pl.off_zero_begin, 0, pl.off_zero_end - pl.off_zero_begin, st));
 
   EncodeParams ep{};
   ep.in = in; ep.emb = m->emb; ep.pe = m->pe; ep.D = m->cfg.embed_dim; ep.Cin = m->Cin; ep.CinPad = m->CinPad;
@@ -810,11 +931,74 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
       const int ns = nb - s0 < pl.S ? nb - s0 : pl.S;
       const long rows = g.rows_of(ns);
       const int num_tiles = (int)((rows + 127) / 128);
-      { DanProfScope ps(DAN_PROF_ENCODE, st); encode_rows_bf16_kernel<<<ns, 256, enc_smem, st>>>(ep, (long)c0 + s0, X0, pl.kstride); }
-      dan_count_launch();
+      if (fast_encode) {
+        DanProfScope ps(DAN_PROF_ENCODE, st);
+        agree_bits_kernel<<<ns, 128, 0, st>>>(in, (long)c0 + s0, P, R, AGREE);
+        encode_prod_bf16_kernel<<<dim3((P + kEncPB - 1) / kEncPB, ns), 256, encode_prod_smem_bytes(R), st>>>(in, m->emb, m->pe, AGREE, (long)c0 + s0, g, X0, pl.kstride);
+        dan_count_launch(2);
+      } else {
+        DanProfScope ps(DAN_PROF_ENCODE, st);
+        encode_rows_bf16_kernel<<<ns, 256, enc_smem, st>>>(ep, (long)c0 + s0, X0, pl.kstride);
+        dan_count_launch();
+      }
       DAN_CUDA_TRY(cudaGetLastError());
       const uint4* cur = X0;
       int hsel = 0;
+      if (fused) {
+        // ---- fused path: one persistent launch per segment of layers without a pool-add in between (dan_stack.cuh) ----
+        int l = 0;
+        while (l < L) {
+          int l_end = l + 1;
+          while (l_end < L && !m->cfg.pool_after[l_end - 1] && l_end - l < kStkMaxSeg) ++l_end;
+          const uint4* seg_in = cur;
+          if (l > 0 && m->cfg.pool_after[l - 1]) {
+            uint4* hp = H[(hsel + 2) % 3];
+            { DanProfScope ps(DAN_PROF_POOL, st); add_pool_bf16_kernel<<<grid_for(rows * kKC), 256, 0, st>>>(cur, POOL, hp, pl.kstride, rows, g); }
+            dan_count_launch();
+            seg_in = hp;
+          }
+          uint4* next = H[(hsel + 1) % 3];
+          StackParams sp{};
+          sp.in = seg_in; sp.in_kstride = pl.kstride; sp.out = next; sp.out_kstride = pl.kstride;
+          sp.t_reads_stride = pl.readsPad; sp.num_reads = ns * R; sp.P = P; sp.pitch = g.pitch; sp.bott = bott > 0 ? bott : 32;
+          sp.num_layers = l_end - l;
+          for (int k = l; k < l_end; ++k) {
+            StackLayer& SL = sp.layer[k - l];
+            SL.wstream = bw->wstream[k]; SL.chan = bw->chan_dev + (size_t)k * 4 * kC; SL.bbias = m->bottB[k];
+            SL.tout = T + (long)k * pl.t_layer_pieces;
+            SL.kc_in = (k == 0 ? m->CinPad : kC) / 8; SL.conv_blocks = 3 * SL.kc_in / 2;
+            SL.dil = m->cfg.dilation[k]; SL.residual = m->cfg.is_residual[k]; SL.highway = m->cfg.highway;
+          }
+          int grid = sp.num_reads / 2 < bw->num_sms ? (sp.num_reads + 1) / 2 : bw->num_sms;
+          static const bool stack_prof = getenv("DAN_B200_STACKPROF") != nullptr;     // development aid: per-role cycle counters
+          if (stack_prof) { DAN_CUDA_TRY(cudaMalloc(&sp.prof, sizeof(unsigned long long) * 12 * grid)); DAN_CUDA_TRY(cudaMemsetAsync(sp.prof, 0, sizeof(unsigned long long) * 12 * grid, st)); }
+          { DanProfScope ps(DAN_PROF_CONV_STACK, st); dan_stack_kernel<<<grid, kStkThreads, kStkSmemBytes, st>>>(sp); }
+          dan_count_launch();
+          DAN_CUDA_TRY(cudaGetLastError());
+          if (stack_prof) {
+            std::vector<unsigned long long> h(12 * (size_t)grid);
+            DAN_CUDA_TRY(cudaStreamSynchronize(st));
+            DAN_CUDA_TRY(cudaMemcpy(h.data(), sp.prof, h.size() * 8, cudaMemcpyDeviceToHost));
+            cudaFree(sp.prof);
+            double a[12] = {0};
+            for (int c = 0; c < grid; ++c) for (int k = 0; k < 12; ++k) a[k] += (double)h[c * 12 + k] / grid;
+            fprintf(stderr, "[stackprof] layers %d-%d reads %d grid %d: issuer total %.0f idle %.0f | epi0 wait %.0f main %.0f bott %.0f | epi1 wait %.0f main %.0f bott %.0f | issue-section %.0f over %.0f stages (cycles, mean over CTAs)\n",
+                    l + 1, l_end, sp.num_reads, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]);
+          }
+          if (m->cfg.pool_after[l_end - 1] && l_end < L) {
+            { DanProfScope ps(DAN_PROF_POOL, st); pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(next, pl.kstride, POOL, g); }
+            dan_count_launch();
+          }
+          cur = next; hsel = (hsel + 1) % 3;
+          l = l_end;
+        }
+        if (m->cfg.highway) {
+          for (int k = 0; k < L; ++k) {
+            rc = run_gemm(T + (long)k * pl.t_layer_pieces, pl.readsPad, bw->wcomp[k], bott, ns * R, bott, P * bott / 8, HW + (long)k * pl.hw_layer_stride, bott, bw->num_sms, st);
+            if (rc) return rc;
+          }
+        }
+      } else
       for (int l = 0; l < L; ++l) {
         const uint4* conv_in = cur;
         if (l > 0 && m->cfg.pool_after[l - 1]) {
@@ -827,7 +1011,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
         uint4* next = H[(hsel + 1) % 3];
         LayerParams lp{};
         lp.in = conv_in; lp.in_kstride = pl.kstride; lp.out = next; lp.out_kstride = pl.kstride;
-        lp.tout = T; lp.t_reads_stride = pl.readsPad;
+        lp.tout = T + (long)l * pl.t_layer_pieces; lp.t_reads_stride = pl.readsPad;
         lp.resid = (m->cfg.is_residual[l] && conv_in != cur) ? cur : nullptr;   // residual excludes the pool term (model.py:732 vs :742)
         lp.wconv = bw->wconv[l]; lp.wres = bw->wres[l]; lp.wbott = bw->wbott[l];
         lp.rows_total = rows; lp.num_tiles = num_tiles; lp.pitch = g.pitch; lp.P = P; lp.gap = g.gap; lp.dil = m->cfg.dilation[l];
@@ -846,7 +1030,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           DAN_CUDA_TRY(cudaGetLastError());
         }
         if (m->cfg.highway) {
-          rc = run_gemm(T, pl.readsPad, bw->wcomp[l], bott, ns * R, bott, P * bott / 8, HW + (long)l * pl.hw_layer_stride, bott, bw->num_sms, st);
+          rc = run_gemm(T + (long)l * pl.t_layer_pieces, pl.readsPad, bw->wcomp[l], bott, ns * R, bott, P * bott / 8, HW + (long)l * pl.hw_layer_stride, bott, bw->num_sms, st);
           if (rc) return rc;
         }
         cur = next; hsel = (hsel + 1) % 3;

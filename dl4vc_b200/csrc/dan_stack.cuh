@@ -1,0 +1,383 @@
+// dan_stack.cuh — fused, persistent conv-stack kernel (bf16 tcgen05). Included by dan_bf16.cu.
+//
+// One launch runs a SEGMENT of consecutive conv layers (a maximal run without a read-axis pool-add in between:
+// PROD = layers 1-2, then layers 3-7; dl4vc/model.py:728-778) for every read of a pass. A read (201 positions x 128
+// channels, bf16) is loaded once into shared memory, goes through all layers of the segment IN PLACE and is written
+// back once; per-read activations between layers never touch HBM.
+//
+// Orientation ("D^T"): for one read and one layer the tensor core computes
+//       D[cout 0..127][position 0..207] = sum_tap  W_tap[cout][cin] * X[position + (tap-1)*dil][cin]
+// i.e. M = 128 output channels (A operand = weights, streamed from L2 through a shared-memory ring), N = 208 positions
+// (B operand = the read's activation buffer; a dilated tap is a row offset of the descriptor start address, the zero
+// rows around the read implement Conv2d's zero padding, model.py:214-229), accumulator = 208 TMEM columns.
+// 201 -> 208 padding costs 3.4 % (a positions-as-M tiling would cost 21 %). The epilogue reads the accumulator in the
+// mma C-fragment layout (tcgen05.ld 16x256b), applies +bias -> ReLU -> BatchNorm with per-thread channel constants
+// (model.py:749-751) and writes bf16 back into the activation buffer with stmatrix.trans, which performs the
+// [channel][position] -> [position][channel] transpose for free.
+// Residual layers (model.py:753-761): the same epilogue pre-loads the accumulator with x + b_res (tcgen05.st), a
+// second MMA pass accumulates W_res * y on top, and a second epilogue writes the layer output.
+// Highway bottleneck (model.py:773-774): positions-as-M orientation (D3[position][32]) so that N = 32 is legal; its
+// epilogue writes relu(.)+bias to the T matrix consumed by the compression GEMM.
+//
+// Per CTA: two independent read pipelines ("slots": own accumulator, own epilogue warpgroup, own weight ring) that
+// the single MMA-issuing thread multiplexes at weight-stage granularity, so one slot's epilogue runs under the other
+// slot's MMAs; three activation buffers rotate so that the next read's load and the previous read's store overlap
+// with compute.
+#pragma once
+
+namespace {
+
+constexpr int kStkThreads = 384;       // warps 0-3 epilogue slot 0 | 4-7 epilogue slot 1 | 8,9 weight producers | 10 MMA issuer | 11 read loader/storer
+constexpr int kStkLead = 2;            // zero rows in front of position 0 (>= largest dilation)
+constexpr int kStkN = 208;             // MMA N = positions per read, padded to a multiple of 16
+constexpr int kStkRB = kStkLead + kStkN + 2;   // rows per channel-chunk plane of a read buffer (212)
+constexpr int kStkPlane = kStkRB * 16;         // bytes per plane (3392)
+constexpr int kStkBuf = kKC * kStkPlane;       // bytes per read buffer (54272)
+constexpr int kStkNumBuf = 3;
+constexpr int kStkStageBytes = 8192;   // weight-ring stage = two k-step blocks of 4 KB
+constexpr int kStkStages = 4;          // stages per slot
+constexpr int kStkMaxSeg = 8;          // layers per segment
+constexpr int kStkSmemHeader = 1024;
+constexpr size_t kStkSmemBytes = kStkSmemHeader + (size_t)kStkNumBuf * kStkBuf + 2 * kStkStages * kStkStageBytes;
+
+struct StackLayer {
+  const uint8_t* wstream;   // conv k-step blocks (tap-major) | residual blocks | bottleneck blocks, contiguous
+  const float* chan;        // [4][128]: conv bias, BN scale, BN shift, residual bias
+  const float* bbias;       // [bott]
+  uint4* tout;              // T[p][c8][read][8] of this layer
+  int conv_blocks;          // 3 * kc_in / 2
+  int kc_in;                // 16-byte pieces per input row (CinPad/8 for layer 1, else 16)
+  int dil, residual, highway;
+};
+
+struct StackParams {
+  const uint4* in; long in_kstride;     // chunk-major input rows (dan_bf16.cu), in_kc planes
+  uint4* out; long out_kstride;         // chunk-major output rows, 16 planes
+  long t_reads_stride;
+  int num_reads, P, pitch, bott, num_layers;
+  unsigned long long* prof;            // optional [grid][12] cycle counters (development aid), or null
+  StackLayer layer[kStkMaxSeg];
+};
+
+struct StackSmem {
+  uint64_t w_full[2][kStkStages], w_empty[2][kStkStages];
+  uint64_t acc_full[2], act_ready[2];
+  uint64_t in_full[kStkNumBuf], out_ready[kStkNumBuf];
+  uint32_t tmem_base;
+};
+
+enum { kEpiFinal = 0, kEpiPreRes = 1, kEpiPostRes = 2 };
+
+// main-accumulator epilogue for one group of NG*8 positions starting at group g0 (see header comment)
+template <int NG, int MODE>
+__device__ __forceinline__ void stack_epi_chunk(uint32_t tbase, uint32_t buf_addr, int g0, int q, int lane, int P,
+                                                const float (&bias)[4], const float (&scale)[4], const float (&shift)[4],
+                                                const float (&rbias)[4]) {
+  uint32_t r0[4 * NG], r1[4 * NG];
+  if constexpr (NG == 4) { tmem_ld_16x256b_x4(tbase + g0 * 8, r0); tmem_ld_16x256b_x4(tbase + (16u << 16) + g0 * 8, r1); }
+  else { tmem_ld_16x256b_x2(tbase + g0 * 8, r0); tmem_ld_16x256b_x2(tbase + (16u << 16) + g0 * 8, r1); }
+  tmem_ld_wait();
+  uint32_t x0[4 * NG], x1[4 * NG];
+#pragma unroll
+  for (int gi = 0; gi < NG; ++gi) {
+    const int g = g0 + gi;
+    const int pos = 8 * g + 2 * (lane & 3);
+    const bool ok0 = pos < P, ok1 = pos + 1 < P;
+    // this thread's row of the four 8x8 blocks (channel chunks 4q..4q+3) of position group g
+    const uint32_t saddr = buf_addr + (uint32_t)(4 * q + (lane >> 3)) * kStkPlane + (uint32_t)(kStkLead + 8 * g + (lane & 7)) * 16;
+    uint32_t pk[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t* src = (j < 2) ? r0 : r1;
+      float lo = __uint_as_float(src[4 * gi + 2 * (j & 1)]), hi = __uint_as_float(src[4 * gi + 2 * (j & 1) + 1]);
+      if constexpr (MODE != kEpiPostRes) {
+        lo = fmaf(fmaxf(lo + bias[j], 0.f), scale[j], shift[j]);      // ReLU, then BatchNorm (model.py:749-751)
+        hi = fmaf(fmaxf(hi + bias[j], 0.f), scale[j], shift[j]);
+      }
+      pk[j] = pack_bf16x2(ok0 ? lo : 0.f, ok1 ? hi : 0.f);
+    }
+    if constexpr (MODE == kEpiPreRes) {
+      uint32_t xin[4];
+      ldmatrix_x4_trans(saddr, xin[0], xin[1], xin[2], xin[3]);        // layer input x (model.py:732), same fragment layout
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t* dst = (j < 2) ? x0 : x1;
+        dst[4 * gi + 2 * (j & 1)] = __float_as_uint(bf16_lo(xin[j]) + rbias[j]);
+        dst[4 * gi + 2 * (j & 1) + 1] = __float_as_uint(bf16_hi(xin[j]) + rbias[j]);
+      }
+    }
+    stmatrix_x4_trans(saddr, pk[0], pk[1], pk[2], pk[3]);
+  }
+  if constexpr (MODE == kEpiPreRes) {     // accumulator := x + b_res; the residual 1x1 MMA accumulates on top (model.py:760-761)
+    if constexpr (NG == 4) { tmem_st_16x256b_x4(tbase + g0 * 8, x0); tmem_st_16x256b_x4(tbase + (16u << 16) + g0 * 8, x1); }
+    else { tmem_st_16x256b_x2(tbase + g0 * 8, x0); tmem_st_16x256b_x2(tbase + (16u << 16) + g0 * 8, x1); }
+  }
+}
+
+template <int MODE>
+__device__ __forceinline__ void stack_epi_main(uint32_t tbase, uint32_t buf_addr, int q, int lane, int P, const float (&bias)[4],
+                                               const float (&scale)[4], const float (&shift)[4], const float (&rbias)[4]) {
+#pragma unroll 1
+  for (int g0 = 0; g0 < 24; g0 += 4) stack_epi_chunk<4, MODE>(tbase, buf_addr, g0, q, lane, P, bias, scale, shift, rbias);
+  stack_epi_chunk<2, MODE>(tbase, buf_addr, 24, q, lane, P, bias, scale, shift, rbias);
+  if constexpr (MODE == kEpiPreRes) tmem_st_wait();
+}
+
+__global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_constant__ StackParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  StackSmem* sm = reinterpret_cast<StackSmem*>(smem);
+  uint8_t* bufs = smem + kStkSmemHeader;
+  uint8_t* rings = bufs + (size_t)kStkNumBuf * kStkBuf;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  const int per = p.num_reads / (int)gridDim.x, rem = p.num_reads % (int)gridDim.x;
+  const int r_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+  const int n_reads = per + ((int)blockIdx.x < rem ? 1 : 0);
+
+  {  // zero rows / planes must read as 0 until an epilogue or a load writes them
+    uint4* z = reinterpret_cast<uint4*>(bufs);
+    for (int i = threadIdx.x; i < kStkNumBuf * kStkBuf / 16; i += kStkThreads) z[i] = make_uint4(0, 0, 0, 0);
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 2; ++s) {
+      for (int i = 0; i < kStkStages; ++i) { mbar_init(&sm->w_full[s][i], 1); mbar_init(&sm->w_empty[s][i], 1); }
+      mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], 128);
+    }
+    for (int b = 0; b < kStkNumBuf; ++b) { mbar_init(&sm->in_full[b], 1); mbar_init(&sm->out_ready[b], 128); }
+    fence_mbar_init();
+  }
+  fence_proxy_async_smem();
+  if (warp == 10) tmem_alloc<512>(&sm->tmem_base);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sm->tmem_base;
+  const uint32_t plane_bytes_in = (uint32_t)p.P * 16;
+
+  if (warp == 11) {
+    // ===================== read loader / storer ==================================================================
+    if (lane == 0) {
+      const int in_kc = p.layer[0].kc_in;
+      auto load_read = [&](int i) {
+        const int b = i % kStkNumBuf;
+        mbar_expect_tx(&sm->in_full[b], plane_bytes_in * in_kc);
+        const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
+        uint8_t* dst = bufs + (size_t)b * kStkBuf + kStkLead * 16;
+        for (int kc = 0; kc < in_kc; ++kc) bulk_g2s(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[b]);
+      };
+      for (int i = 0; i < n_reads && i < kStkNumBuf; ++i) load_read(i);
+      for (int i = 0; i < n_reads; ++i) {
+        const int b = i % kStkNumBuf;
+        mbar_wait(&sm->out_ready[b], (i / kStkNumBuf) & 1);
+        uint4* dst = p.out + kLead + (long)(r_begin + i) * p.pitch;
+        const uint8_t* src = bufs + (size_t)b * kStkBuf + kStkLead * 16;
+        for (int kc = 0; kc < kKC; ++kc) bulk_s2g(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in);
+        bulk_commit();
+        bulk_wait_read0();
+        if (i + kStkNumBuf < n_reads) load_read(i + kStkNumBuf);
+      }
+      bulk_wait0();
+    }
+  } else if (warp == 8 || warp == 9) {
+    // ===================== weight producer of slot s: streams every op's A/B blocks in issue order =================
+    if (lane == 0) {
+      const int s = warp - 8;
+      uint8_t* ring = rings + (size_t)s * kStkStages * kStkStageBytes;
+      uint32_t c = 0;
+      auto emit = [&](const uint8_t* src, uint32_t bytes) {
+        for (uint32_t off = 0; off < bytes; off += kStkStageBytes, ++c) {
+          const uint32_t idx = c % kStkStages, n = min((uint32_t)kStkStageBytes, bytes - off);
+          mbar_wait(&sm->w_empty[s][idx], ((c / kStkStages) & 1) ^ 1);
+          mbar_expect_tx(&sm->w_full[s][idx], n);
+          bulk_g2s(ring + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[s][idx]);
+        }
+      };
+      for (int i = s; i < n_reads; i += 2) {
+        for (int l = 0; l < p.num_layers; ++l) {
+          const StackLayer& L = p.layer[l];
+          const uint32_t conv_bytes = (uint32_t)L.conv_blocks * 4096u;
+          emit(L.wstream, conv_bytes);
+          if (L.residual) emit(L.wstream + conv_bytes, kKC / 2 * 4096u);
+          if (L.highway) emit(L.wstream + conv_bytes + (L.residual ? kKC / 2 * 4096u : 0u), (uint32_t)kKC * p.bott * 16u);
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // ===================== MMA issuer: the whole warp runs two slot state machines in lock-step (warp-uniform control
+    // flow keeps descriptors in uniform registers); one elected lane issues the tcgen05 instructions ==================
+    {
+      const uint32_t idesc_main = make_idesc_bf16(128, kStkN);
+      const uint32_t idesc_bott = make_idesc_bf16(128, p.bott);
+      const uint32_t bott_block = (uint32_t)p.bott * 32u;       // bytes of one bottleneck k-step block
+      const uint32_t bufs_addr = smem_u32(bufs), rings_addr = smem_u32(rings);
+      int rd[2] = {0, 1}, ly[2] = {0, 0}, kind[2] = {0, 0}, blk[2] = {0, 0}, tap[2] = {0, 0}, jj[2] = {0, 0};
+      uint32_t opc[2] = {0, 0}, wc[2] = {0, 0}, widx[2] = {0, 0};
+      bool started[2] = {false, false};
+      bool active[2] = {n_reads > 0, n_reads > 1};
+      uint32_t idle = 0;
+      const long long t_begin = clock64();
+      long long t_idle = 0, t_mark = t_begin, t_issue = 0, n_issue = 0;
+      while (active[0] || active[1]) {
+        bool progressed = false;
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          if (!active[s]) continue;
+          const StackLayer& L = p.layer[ly[s]];
+          const int b = rd[s] % kStkNumBuf;
+          if (!started[s]) {
+            bool ok = false;
+            if (lane == 0) {
+              ok = mbar_test_wait(&sm->act_ready[s], opc[s] & 1);
+              if (ok && ly[s] == 0 && kind[s] == 0) ok = mbar_test_wait(&sm->in_full[b], (rd[s] / kStkNumBuf) & 1);
+            }
+            if (!__any_sync(0xffffffffu, ok)) continue;
+            started[s] = true;
+          }
+          {
+            bool ok = false;
+            if (lane == 0) ok = mbar_test_wait(&sm->w_full[s][widx[s]], (wc[s] / kStkStages) & 1);
+            if (!__any_sync(0xffffffffu, ok)) continue;
+          }
+          tc_fence_after();
+          progressed = true;
+          long long t_i0 = 0;
+          if (p.prof) t_i0 = clock64();
+          const int total = kind[s] == 0 ? L.conv_blocks : kKC / 2;
+          const uint32_t bbytes = kind[s] == 2 ? bott_block : 4096u;
+          const int per_stage = kind[s] == 2 ? (int)(kStkStageBytes / bott_block) : kStkStageBytes / 4096;
+          const int nb = min(per_stage, total - blk[s]);
+          const uint32_t buf_addr = bufs_addr + (uint32_t)b * kStkBuf;
+          const uint32_t stage_addr = rings_addr + ((uint32_t)s * kStkStages + widx[s]) * kStkStageBytes;
+          const uint32_t d_main = tmem_base + (uint32_t)s * 256u;
+          const int ksteps = L.kc_in / 2;
+          for (int i = 0; i < nb; ++i) {
+            const int k = blk[s] + i;
+            if (kind[s] == 0) {
+              const uint32_t xb = buf_addr + (uint32_t)(2 * jj[s]) * kStkPlane + (uint32_t)(kStkLead + (tap[s] - 1) * L.dil) * 16;
+              const uint64_t ad = make_smem_desc(stage_addr + i * 4096u, 2048, 128), bd = make_smem_desc(xb, kStkPlane, 128);
+              if (elect_one()) umma_bf16(d_main, ad, bd, idesc_main, k > 0);
+              if (++jj[s] == ksteps) { jj[s] = 0; ++tap[s]; }
+            } else if (kind[s] == 1) {
+              const uint32_t xb = buf_addr + (uint32_t)(2 * k) * kStkPlane + (uint32_t)kStkLead * 16;
+              const uint64_t ad = make_smem_desc(stage_addr + i * 4096u, 2048, 128), bd = make_smem_desc(xb, kStkPlane, 128);
+              if (elect_one()) umma_bf16(d_main, ad, bd, idesc_main, 1);
+            } else {
+              const uint32_t xa = buf_addr + (uint32_t)(2 * k) * kStkPlane + (uint32_t)kStkLead * 16;
+              const uint64_t a0d = make_smem_desc(xa, kStkPlane, 128), a1d = make_smem_desc(xa + 128 * 16, kStkPlane, 128);
+              const uint64_t bd = make_smem_desc(stage_addr + i * bbytes, (uint32_t)p.bott * 16, 128);
+              if (elect_one()) {
+                umma_bf16(d_main, a0d, bd, idesc_bott, k > 0);
+                umma_bf16(d_main + (uint32_t)p.bott, a1d, bd, idesc_bott, k > 0);
+              }
+            }
+            __syncwarp();
+          }
+          if (elect_one()) umma_commit(&sm->w_empty[s][widx[s]]);
+          __syncwarp();
+          ++wc[s];
+          if (++widx[s] == kStkStages) widx[s] = 0;
+          blk[s] += nb;
+          if (p.prof) { t_issue += clock64() - t_i0; ++n_issue; }
+          if (blk[s] == total) {
+            if (elect_one()) umma_commit(&sm->acc_full[s]);
+            __syncwarp();
+            ++opc[s]; started[s] = false; blk[s] = 0; tap[s] = 0; jj[s] = 0;
+            int nk = -1;
+            if (kind[s] == 0) nk = L.residual ? 1 : (L.highway ? 2 : -1);
+            else if (kind[s] == 1) nk = L.highway ? 2 : -1;
+            if (nk >= 0) kind[s] = nk;
+            else {
+              kind[s] = 0;
+              if (++ly[s] == p.num_layers) { ly[s] = 0; rd[s] += 2; if (rd[s] >= n_reads) active[s] = false; }
+            }
+          }
+        }
+        if (p.prof) { const long long now = clock64(); if (!progressed) t_idle += now - t_mark; t_mark = now; }
+        if (progressed) idle = 0;
+        else if (++idle > (1u << 27)) __trap();     // a protocol bug must fail the launch, not hang the GPU
+      }
+      if (p.prof && lane == 0) { p.prof[blockIdx.x * 12 + 0] = clock64() - t_begin; p.prof[blockIdx.x * 12 + 1] = t_idle; p.prof[blockIdx.x * 12 + 8] = t_issue; p.prof[blockIdx.x * 12 + 9] = n_issue; }
+    }
+  } else {
+    // ===================== epilogue warpgroups =======================================================================
+    const int s = warp >> 2, q = warp & 3;
+    const uint32_t tbase = tmem_base + (uint32_t)s * 256u + ((uint32_t)(32 * q) << 16);
+    mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
+    uint32_t opc = 0;
+    long long t_wait = 0, t_main = 0, t_bott = 0, t0 = 0;
+    const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0;
+    for (int i = s; i < n_reads; i += 2) {
+      const int b = i % kStkNumBuf;
+      const uint32_t buf_addr = smem_u32(bufs + (size_t)b * kStkBuf);
+      for (int l = 0; l < p.num_layers; ++l) {
+        const StackLayer& L = p.layer[l];
+        float bias[4], scale[4], shift[4], rbias[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int c = 32 * q + 8 * j + (lane >> 2);
+          bias[j] = __ldg(L.chan + c); scale[j] = __ldg(L.chan + kC + c); shift[j] = __ldg(L.chan + 2 * kC + c); rbias[j] = __ldg(L.chan + 3 * kC + c);
+        }
+        if (prof) t0 = clock64();
+        mbar_wait(&sm->acc_full[s], opc & 1);
+        tc_fence_after();
+        if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+        if (L.residual) stack_epi_main<kEpiPreRes>(tbase, buf_addr, q, lane, p.P, bias, scale, shift, rbias);
+        else stack_epi_main<kEpiFinal>(tbase, buf_addr, q, lane, p.P, bias, scale, shift, rbias);
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&sm->act_ready[s]);
+        ++opc;
+        if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
+        if (L.residual) {
+          mbar_wait(&sm->acc_full[s], opc & 1);
+          tc_fence_after();
+          if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+          stack_epi_main<kEpiPostRes>(tbase, buf_addr, q, lane, p.P, bias, scale, shift, rbias);
+          fence_proxy_async_smem();
+          tc_fence_before();
+          mbar_arrive(&sm->act_ready[s]);
+          ++opc;
+          if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
+        }
+        if (L.highway) {
+          mbar_wait(&sm->acc_full[s], opc & 1);
+          tc_fence_after();
+          if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+          const int c8n = p.bott / 8;
+          for (int tile = 0; tile < 2; ++tile) {
+            const int pos = 128 * tile + 32 * q + lane;
+            for (int cc = 0; cc < p.bott / 32; ++cc) {
+              uint32_t r[32];
+              tmem_ld32(tbase + (uint32_t)(tile * p.bott + cc * 32), r);
+              tmem_ld_wait();
+              if (pos < p.P) {
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(L.bbias + cc * 32 + g * 8));
+                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(L.bbias + cc * 32 + g * 8 + 4));
+                  uint4 o;                                                                 // relu(bottleneck), model.py:774
+                  o.x = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(r[g * 8 + 1]) + b0.y, 0.f));
+                  o.y = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(r[g * 8 + 3]) + b0.w, 0.f));
+                  o.z = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(r[g * 8 + 5]) + b1.y, 0.f));
+                  o.w = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(r[g * 8 + 7]) + b1.w, 0.f));
+                  L.tout[((long)pos * c8n + cc * 4 + g) * p.t_reads_stride + (r_begin + i)] = o;
+                }
+              }
+            }
+          }
+          tc_fence_before();
+          mbar_arrive(&sm->act_ready[s]);
+          ++opc;
+          if (prof) { const long long t1 = clock64(); t_bott += t1 - t0; t0 = t1; }
+        }
+      }
+      mbar_arrive(&sm->out_ready[b]);       // every MMA and epilogue of this read is done: the buffer may be stored and refilled
+    }
+    if (prof) { unsigned long long* d = p.prof + blockIdx.x * 12 + 2 + 3 * s; d[0] = t_wait; d[1] = t_main; d[2] = t_bott; }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 10) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace
