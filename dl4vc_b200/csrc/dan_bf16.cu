@@ -26,7 +26,11 @@ using namespace ptx;
 
 constexpr int kC = 128;               // channels (bf16 path is specialised for the shipped width)
 constexpr int kKC = kC / 8;           // 16-byte pieces per row
-constexpr int kLead = 8;              // zero rows in front of every row matrix (>= largest dilation)
+constexpr int kLead = 8;
+// Every CTA of the fused kernel streams the same few hundred KB of layer weights at about the same time; with a single
+// copy those reads pile up on the handful of L2 slices that own the current lines (measured: 8 KB per ~950 cycles per
+// SM). CTA c therefore reads replica c % kWeightReplicas.
+constexpr int kWeightReplicas = 16;              // zero rows in front of every row matrix (>= largest dilation)
 
 // =====================================================================================================
 // Encoder (bf16, chunk-major output)
@@ -686,7 +690,8 @@ struct Bf16Weights {
   uint4* wconv[DAN_MAX_LAYERS]; uint4* wres[DAN_MAX_LAYERS]; uint4* wbott[DAN_MAX_LAYERS]; uint4* wcomp[DAN_MAX_LAYERS];
   uint4* fcw[DAN_MAX_FC]; uint4* headw;
   const float** comp_bias_ptrs;       // device array of L pointers
-  uint8_t* wstream[DAN_MAX_LAYERS];   // conv | residual | bottleneck operand images of a layer, contiguous (dan_stack.cuh)
+  uint8_t* wstream[DAN_MAX_LAYERS];   // conv | residual | bottleneck operand images of a layer, contiguous (dan_stack.cuh); kWeightReplicas copies
+  size_t wstream_bytes[DAN_MAX_LAYERS];   // bytes of one copy (256-byte multiple)
   float* chan_dev;                    // [L][4][128] conv bias, BN scale, BN shift, residual bias (device)
   // host copies of the per-channel epilogue constants (kernel parameters -> constant bank)
   float bias[DAN_MAX_LAYERS][kC], scale[DAN_MAX_LAYERS][kC], shift[DAN_MAX_LAYERS][kC], rbias[DAN_MAX_LAYERS][kC], bbias[DAN_MAX_LAYERS][64];
@@ -814,7 +819,8 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
     const int cin = l == 0 ? m->Cin : kC, kc_in = (l == 0 ? m->CinPad : kC) / 8;
     if (!bw->wstream[l]) {
       const size_t conv_b = (size_t)3 * kc_in * kC * 16, res_b = m->cfg.is_residual[l] ? (size_t)kKC * kC * 16 : 0, bott_b = m->cfg.highway ? (size_t)kKC * bott * 16 : 0;
-      DAN_CUDA_TRY(cudaMalloc(&bw->wstream[l], conv_b + res_b + bott_b + 16));
+      bw->wstream_bytes[l] = round_up_z(conv_b + res_b + bott_b, 256);
+      DAN_CUDA_TRY(cudaMalloc(&bw->wstream[l], bw->wstream_bytes[l] * kWeightReplicas));
       bw->wconv[l] = reinterpret_cast<uint4*>(bw->wstream[l]);
       if (res_b) bw->wres[l] = reinterpret_cast<uint4*>(bw->wstream[l] + conv_b);
       if (bott_b) bw->wbott[l] = reinterpret_cast<uint4*>(bw->wstream[l] + conv_b + res_b);
@@ -840,6 +846,9 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
   }
   if ((rc = alloc(&bw->headw, (size_t)(m->hidden / 8) * DAN_HEAD_PAD))) return rc;
   pack_linear_bf16_kernel<<<grid_for((long)m->hidden * DAN_HEAD_PAD), 256, 0, st>>>(w->head_w, bw->headw, DAN_NUM_HEAD_OUTPUTS, DAN_HEAD_PAD, m->hidden, m->hidden, 0, P, kC, R, bott, L, 0, 0);
+  for (int l = 0; l < L; ++l)
+    for (int r = 1; r < kWeightReplicas; ++r)
+      DAN_CUDA_TRY(cudaMemcpyAsync(bw->wstream[l] + (size_t)r * bw->wstream_bytes[l], bw->wstream[l], bw->wstream_bytes[l], cudaMemcpyDeviceToDevice, st));
   DAN_CUDA_TRY(cudaGetLastError());
   // epilogue constants -> host (the fp32 packer already folded BatchNorm on this stream)
   DAN_CUDA_TRY(cudaStreamSynchronize(st));
@@ -964,26 +973,39 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           sp.num_layers = l_end - l;
           for (int k = l; k < l_end; ++k) {
             StackLayer& SL = sp.layer[k - l];
-            SL.wstream = bw->wstream[k]; SL.chan = bw->chan_dev + (size_t)k * 4 * kC; SL.bbias = m->bottB[k];
+            SL.wstream = bw->wstream[k]; SL.wreplica_stride = bw->wstream_bytes[k]; SL.chan = bw->chan_dev + (size_t)k * 4 * kC; SL.bbias = m->bottB[k];
             SL.tout = T + (long)k * pl.t_layer_pieces;
             SL.kc_in = (k == 0 ? m->CinPad : kC) / 8; SL.conv_blocks = 3 * SL.kc_in / 2;
             SL.dil = m->cfg.dilation[k]; SL.residual = m->cfg.is_residual[k]; SL.highway = m->cfg.highway;
           }
           int grid = sp.num_reads / 2 < bw->num_sms ? (sp.num_reads + 1) / 2 : bw->num_sms;
+          static const int stack_debug = getenv("DAN_B200_STACKDEBUG") ? atoi(getenv("DAN_B200_STACKDEBUG")) : 0;
+          sp.debug = stack_debug;
           static const bool stack_prof = getenv("DAN_B200_STACKPROF") != nullptr;     // development aid: per-role cycle counters
-          if (stack_prof) { DAN_CUDA_TRY(cudaMalloc(&sp.prof, sizeof(unsigned long long) * 12 * grid)); DAN_CUDA_TRY(cudaMemsetAsync(sp.prof, 0, sizeof(unsigned long long) * 12 * grid, st)); }
+          static const bool stack_trace = getenv("DAN_B200_STACKTRACE") != nullptr;
+          static int trace_dumps = 0;
+          if (stack_trace && trace_dumps < 2 && sp.num_layers > 2) { sp.trace_cap = 6000; DAN_CUDA_TRY(cudaMalloc(&sp.trace, sizeof(uint2) * sp.trace_cap)); DAN_CUDA_TRY(cudaMemsetAsync(sp.trace, 0, sizeof(uint2) * sp.trace_cap, st)); }
+          if (stack_prof) { DAN_CUDA_TRY(cudaMalloc(&sp.prof, sizeof(unsigned long long) * 16 * grid)); DAN_CUDA_TRY(cudaMemsetAsync(sp.prof, 0, sizeof(unsigned long long) * 16 * grid, st)); }
           { DanProfScope ps(DAN_PROF_CONV_STACK, st); dan_stack_kernel<<<grid, kStkThreads, kStkSmemBytes, st>>>(sp); }
           dan_count_launch();
           DAN_CUDA_TRY(cudaGetLastError());
+          if (sp.trace) {
+            std::vector<uint2> h(sp.trace_cap);
+            DAN_CUDA_TRY(cudaStreamSynchronize(st));
+            DAN_CUDA_TRY(cudaMemcpy(h.data(), sp.trace, h.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
+            cudaFree(sp.trace);
+            char name[64]; snprintf(name, sizeof(name), "gpurun_out/stack_trace_%d.txt", trace_dumps++);
+            if (FILE* f = fopen(name, "w")) { const int n = (int)h[0].x < sp.trace_cap - 1 ? (int)h[0].x : sp.trace_cap - 1; for (int k = 1; k <= n; ++k) fprintf(f, "%x %u\n", h[k].x, h[k].y); fclose(f); }
+          }
           if (stack_prof) {
-            std::vector<unsigned long long> h(12 * (size_t)grid);
+            std::vector<unsigned long long> h(16 * (size_t)grid);
             DAN_CUDA_TRY(cudaStreamSynchronize(st));
             DAN_CUDA_TRY(cudaMemcpy(h.data(), sp.prof, h.size() * 8, cudaMemcpyDeviceToHost));
             cudaFree(sp.prof);
-            double a[12] = {0};
-            for (int c = 0; c < grid; ++c) for (int k = 0; k < 12; ++k) a[k] += (double)h[c * 12 + k] / grid;
-            fprintf(stderr, "[stackprof] layers %d-%d reads %d grid %d: issuer total %.0f idle %.0f | epi0 wait %.0f main %.0f bott %.0f | epi1 wait %.0f main %.0f bott %.0f | issue-section %.0f over %.0f stages (cycles, mean over CTAs)\n",
-                    l + 1, l_end, sp.num_reads, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9]);
+            double a[16] = {0};
+            for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)h[c * 16 + k] / grid;
+            fprintf(stderr, "[stackprof] layers %d-%d reads %d grid %d: issuer0 total %.0f dep-wait %.0f | epi0 wait %.0f main %.0f bott %.0f | epi1 wait %.0f main %.0f bott %.0f | store+load wait %.0f %.0f | issuer1 total %.0f dep-wait %.0f (cycles, mean over CTAs)\n",
+                    l + 1, l_end, sp.num_reads, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]);
           }
           if (m->cfg.pool_after[l_end - 1] && l_end < L) {
             { DanProfScope ps(DAN_PROF_POOL, st); pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(next, pl.kstride, POOL, g); }

@@ -27,21 +27,21 @@
 
 namespace {
 
-constexpr int kStkThreads = 384;       // warps 0-3 epilogue slot 0 | 4-7 epilogue slot 1 | 8,9 weight producers | 10 MMA issuer | 11 read loader/storer
+constexpr int kStkThreads = 384;       // warps 0-3 epilogue slot 0 | 4-7 epilogue slot 1 | 8,9 weight producers | 10,11 MMA issuers
 constexpr int kStkLead = 2;            // zero rows in front of position 0 (>= largest dilation)
 constexpr int kStkN = 208;             // MMA N = positions per read, padded to a multiple of 16
 constexpr int kStkRB = kStkLead + kStkN + 2;   // rows per channel-chunk plane of a read buffer (212)
 constexpr int kStkPlane = kStkRB * 16;         // bytes per plane (3392)
 constexpr int kStkBuf = kKC * kStkPlane;       // bytes per read buffer (54272)
-constexpr int kStkNumBuf = 3;
 constexpr int kStkStageBytes = 8192;   // weight-ring stage = two k-step blocks of 4 KB
-constexpr int kStkStages = 4;          // stages per slot
+constexpr int kStkStages = 7;          // stages per slot
 constexpr int kStkMaxSeg = 8;          // layers per segment
 constexpr int kStkSmemHeader = 1024;
-constexpr size_t kStkSmemBytes = kStkSmemHeader + (size_t)kStkNumBuf * kStkBuf + 2 * kStkStages * kStkStageBytes;
+constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + 2 * kStkStages * kStkStageBytes + 1024;   // + slack read by the bottleneck A tiles
 
 struct StackLayer {
   const uint8_t* wstream;   // conv k-step blocks (tap-major) | residual blocks | bottleneck blocks, contiguous
+  size_t wreplica_stride;   // byte distance between the kWeightReplicas copies of wstream
   const float* chan;        // [4][128]: conv bias, BN scale, BN shift, residual bias
   const float* bbias;       // [bott]
   uint4* tout;              // T[p][c8][read][8] of this layer
@@ -55,14 +55,15 @@ struct StackParams {
   uint4* out; long out_kstride;         // chunk-major output rows, 16 planes
   long t_reads_stride;
   int num_reads, P, pitch, bott, num_layers;
-  unsigned long long* prof;            // optional [grid][12] cycle counters (development aid), or null
+  unsigned long long* prof;            // optional [grid][16] cycle counters (development aid), or null
+  uint2* trace; int trace_cap;         // development: event trace of CTA 0 (id, clock), trace[0].x = count
+  int debug;                           // development: bit 0 = skip the MMAs, bit 1 = skip epilogue math/stores
   StackLayer layer[kStkMaxSeg];
 };
 
 struct StackSmem {
   uint64_t w_full[2][kStkStages], w_empty[2][kStkStages];
-  uint64_t acc_full[2], act_ready[2];
-  uint64_t in_full[kStkNumBuf], out_ready[kStkNumBuf];
+  uint64_t acc_full[2], act_ready[2], in_full[2];
   uint32_t tmem_base;
 };
 
@@ -123,27 +124,38 @@ __device__ __forceinline__ void stack_epi_main(uint32_t tbase, uint32_t buf_addr
   if constexpr (MODE == kEpiPreRes) tmem_st_wait();
 }
 
+// descriptor words: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14  (tcgen05_ptx.cuh make_smem_desc)
+__device__ __forceinline__ uint64_t stk_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
+
+__device__ __forceinline__ void stk_trace(const StackParams& p, uint32_t id) {
+  if (p.trace && blockIdx.x == 0) {
+    const uint32_t k = atomicAdd(&p.trace[0].x, 1u) + 1;
+    if ((int)k < p.trace_cap) p.trace[k] = make_uint2(id, (uint32_t)clock64());
+  }
+}
+
 __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_constant__ StackParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   StackSmem* sm = reinterpret_cast<StackSmem*>(smem);
   uint8_t* bufs = smem + kStkSmemHeader;
-  uint8_t* rings = bufs + (size_t)kStkNumBuf * kStkBuf;
+  uint8_t* rings = bufs + 2 * (size_t)kStkBuf;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   const int per = p.num_reads / (int)gridDim.x, rem = p.num_reads % (int)gridDim.x;
   const int r_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
   const int n_reads = per + ((int)blockIdx.x < rem ? 1 : 0);
+  const uint32_t plane_bytes_in = (uint32_t)p.P * 16;
+  const int in_kc = p.layer[0].kc_in;
 
   {  // zero rows / planes must read as 0 until an epilogue or a load writes them
     uint4* z = reinterpret_cast<uint4*>(bufs);
-    for (int i = threadIdx.x; i < kStkNumBuf * kStkBuf / 16; i += kStkThreads) z[i] = make_uint4(0, 0, 0, 0);
+    for (int i = threadIdx.x; i < 2 * kStkBuf / 16; i += kStkThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       for (int i = 0; i < kStkStages; ++i) { mbar_init(&sm->w_full[s][i], 1); mbar_init(&sm->w_empty[s][i], 1); }
-      mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], 128);
+      mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], 128); mbar_init(&sm->in_full[s], 1);
     }
-    for (int b = 0; b < kStkNumBuf; ++b) { mbar_init(&sm->in_full[b], 1); mbar_init(&sm->out_ready[b], 128); }
     fence_mbar_init();
   }
   fence_proxy_async_smem();
@@ -152,163 +164,180 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
-  const uint32_t plane_bytes_in = (uint32_t)p.P * 16;
 
-  if (warp == 11) {
-    // ===================== read loader / storer ==================================================================
-    if (lane == 0) {
-      const int in_kc = p.layer[0].kc_in;
-      auto load_read = [&](int i) {
-        const int b = i % kStkNumBuf;
-        mbar_expect_tx(&sm->in_full[b], plane_bytes_in * in_kc);
-        const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
-        uint8_t* dst = bufs + (size_t)b * kStkBuf + kStkLead * 16;
-        for (int kc = 0; kc < in_kc; ++kc) bulk_g2s(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[b]);
-      };
-      for (int i = 0; i < n_reads && i < kStkNumBuf; ++i) load_read(i);
-      for (int i = 0; i < n_reads; ++i) {
-        const int b = i % kStkNumBuf;
-        mbar_wait(&sm->out_ready[b], (i / kStkNumBuf) & 1);
-        uint4* dst = p.out + kLead + (long)(r_begin + i) * p.pitch;
-        const uint8_t* src = bufs + (size_t)b * kStkBuf + kStkLead * 16;
-        for (int kc = 0; kc < kKC; ++kc) bulk_s2g(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in);
-        bulk_commit();
-        bulk_wait_read0();
-        if (i + kStkNumBuf < n_reads) load_read(i + kStkNumBuf);
-      }
-      bulk_wait0();
-    }
-  } else if (warp == 8 || warp == 9) {
+  // global -> shared load of local read i into its slot's buffer (one elected thread)
+  auto load_read = [&](int i) {
+    const int s = i & 1;
+    mbar_expect_tx(&sm->in_full[s], plane_bytes_in * in_kc);
+    const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
+    uint8_t* dst = bufs + (size_t)s * kStkBuf + kStkLead * 16;
+    for (int kc = 0; kc < in_kc; ++kc) bulk_g2s(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s]);
+  };
+
+  if (warp == 8 || warp == 9) {
     // ===================== weight producer of slot s: streams every op's A/B blocks in issue order =================
     if (lane == 0) {
       const int s = warp - 8;
       uint8_t* ring = rings + (size_t)s * kStkStages * kStkStageBytes;
-      uint32_t c = 0;
+      uint32_t idx = 0, par = 1;     // first pass over the ring: the "empty" phase counts as complete
       auto emit = [&](const uint8_t* src, uint32_t bytes) {
-        for (uint32_t off = 0; off < bytes; off += kStkStageBytes, ++c) {
-          const uint32_t idx = c % kStkStages, n = min((uint32_t)kStkStageBytes, bytes - off);
-          mbar_wait(&sm->w_empty[s][idx], ((c / kStkStages) & 1) ^ 1);
+        for (uint32_t off = 0; off < bytes; off += kStkStageBytes) {
+          const uint32_t n = min((uint32_t)kStkStageBytes, bytes - off);
+          mbar_wait(&sm->w_empty[s][idx], par);
           mbar_expect_tx(&sm->w_full[s][idx], n);
           bulk_g2s(ring + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[s][idx]);
+          if (++idx == kStkStages) { idx = 0; par ^= 1; }
         }
       };
       for (int i = s; i < n_reads; i += 2) {
         for (int l = 0; l < p.num_layers; ++l) {
           const StackLayer& L = p.layer[l];
           const uint32_t conv_bytes = (uint32_t)L.conv_blocks * 4096u;
-          emit(L.wstream, conv_bytes);
-          if (L.residual) emit(L.wstream + conv_bytes, kKC / 2 * 4096u);
-          if (L.highway) emit(L.wstream + conv_bytes + (L.residual ? kKC / 2 * 4096u : 0u), (uint32_t)kKC * p.bott * 16u);
+          const uint8_t* w = L.wstream + (size_t)(blockIdx.x % kWeightReplicas) * L.wreplica_stride;
+          emit(w, conv_bytes);
+          if (L.residual) emit(w + conv_bytes, kKC / 2 * 4096u);
+          if (L.highway) emit(w + conv_bytes + (L.residual ? kKC / 2 * 4096u : 0u), (uint32_t)kKC * p.bott * 16u);
         }
       }
     }
-  } else if (warp == 10) {
-    // ===================== MMA issuer: the whole warp runs two slot state machines in lock-step (warp-uniform control
-    // flow keeps descriptors in uniform registers); one elected lane issues the tcgen05 instructions ==================
-    {
-      const uint32_t idesc_main = make_idesc_bf16(128, kStkN);
-      const uint32_t idesc_bott = make_idesc_bf16(128, p.bott);
-      const uint32_t bott_block = (uint32_t)p.bott * 32u;       // bytes of one bottleneck k-step block
-      const uint32_t bufs_addr = smem_u32(bufs), rings_addr = smem_u32(rings);
-      int rd[2] = {0, 1}, ly[2] = {0, 0}, kind[2] = {0, 0}, blk[2] = {0, 0}, tap[2] = {0, 0}, jj[2] = {0, 0};
-      uint32_t opc[2] = {0, 0}, wc[2] = {0, 0}, widx[2] = {0, 0};
-      bool started[2] = {false, false};
-      bool active[2] = {n_reads > 0, n_reads > 1};
-      uint32_t idle = 0;
-      const long long t_begin = clock64();
-      long long t_idle = 0, t_mark = t_begin, t_issue = 0, n_issue = 0;
-      while (active[0] || active[1]) {
-        bool progressed = false;
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-          if (!active[s]) continue;
-          const StackLayer& L = p.layer[ly[s]];
-          const int b = rd[s] % kStkNumBuf;
-          if (!started[s]) {
-            bool ok = false;
-            if (lane == 0) {
-              ok = mbar_test_wait(&sm->act_ready[s], opc[s] & 1);
-              if (ok && ly[s] == 0 && kind[s] == 0) ok = mbar_test_wait(&sm->in_full[b], (rd[s] / kStkNumBuf) & 1);
-            }
-            if (!__any_sync(0xffffffffu, ok)) continue;
-            started[s] = true;
-          }
-          {
-            bool ok = false;
-            if (lane == 0) ok = mbar_test_wait(&sm->w_full[s][widx[s]], (wc[s] / kStkStages) & 1);
-            if (!__any_sync(0xffffffffu, ok)) continue;
-          }
-          tc_fence_after();
-          progressed = true;
-          long long t_i0 = 0;
-          if (p.prof) t_i0 = clock64();
-          const int total = kind[s] == 0 ? L.conv_blocks : kKC / 2;
-          const uint32_t bbytes = kind[s] == 2 ? bott_block : 4096u;
-          const int per_stage = kind[s] == 2 ? (int)(kStkStageBytes / bott_block) : kStkStageBytes / 4096;
-          const int nb = min(per_stage, total - blk[s]);
-          const uint32_t buf_addr = bufs_addr + (uint32_t)b * kStkBuf;
-          const uint32_t stage_addr = rings_addr + ((uint32_t)s * kStkStages + widx[s]) * kStkStageBytes;
-          const uint32_t d_main = tmem_base + (uint32_t)s * 256u;
-          const int ksteps = L.kc_in / 2;
-          for (int i = 0; i < nb; ++i) {
-            const int k = blk[s] + i;
-            if (kind[s] == 0) {
-              const uint32_t xb = buf_addr + (uint32_t)(2 * jj[s]) * kStkPlane + (uint32_t)(kStkLead + (tap[s] - 1) * L.dil) * 16;
-              const uint64_t ad = make_smem_desc(stage_addr + i * 4096u, 2048, 128), bd = make_smem_desc(xb, kStkPlane, 128);
-              if (elect_one()) umma_bf16(d_main, ad, bd, idesc_main, k > 0);
-              if (++jj[s] == ksteps) { jj[s] = 0; ++tap[s]; }
-            } else if (kind[s] == 1) {
-              const uint32_t xb = buf_addr + (uint32_t)(2 * k) * kStkPlane + (uint32_t)kStkLead * 16;
-              const uint64_t ad = make_smem_desc(stage_addr + i * 4096u, 2048, 128), bd = make_smem_desc(xb, kStkPlane, 128);
-              if (elect_one()) umma_bf16(d_main, ad, bd, idesc_main, 1);
-            } else {
-              const uint32_t xa = buf_addr + (uint32_t)(2 * k) * kStkPlane + (uint32_t)kStkLead * 16;
-              const uint64_t a0d = make_smem_desc(xa, kStkPlane, 128), a1d = make_smem_desc(xa + 128 * 16, kStkPlane, 128);
-              const uint64_t bd = make_smem_desc(stage_addr + i * bbytes, (uint32_t)p.bott * 16, 128);
+  } else if (warp == 10 || warp == 11) {
+    // ===================== MMA issuer of slot s. The whole warp runs the (blocking, strictly sequential) op schedule of
+    // its slot — warp-uniform control flow keeps descriptors in uniform registers — and one elected lane issues the
+    // tcgen05 instructions. The two slots' issuers are independent warps: the tensor pipe interleaves their MMA
+    // streams, so one slot's epilogue runs under the other slot's MMAs without any software multiplexing. A single
+    // warp retires one dependent instruction every ~4 cycles, so the loops below are kept to a few instructions
+    // per MMA (descriptor words are advanced by constants). =========================================================
+    const int s = warp - 10;
+    const uint32_t idesc_main = make_idesc_bf16(128, kStkN);
+    const uint32_t idesc_bott = make_idesc_bf16(128, p.bott);
+    const uint32_t desc_hi = (128u >> 4) | (1u << 14);
+    const uint32_t a_lbo_w = (2048u >> 4) << 16, b_lbo_x = ((uint32_t)kStkPlane >> 4) << 16, b_lbo_bott = (((uint32_t)p.bott * 16u) >> 4) << 16;
+    const int bott_per_stage = kStkStageBytes / (p.bott * 32);
+    const uint32_t ring_lo = (smem_u32(rings) >> 4) + (uint32_t)s * kStkStages * (kStkStageBytes >> 4);
+    uint64_t* const wfull = &sm->w_full[s][0];
+    uint64_t* const wempty = &sm->w_empty[s][0];
+    const uint32_t d_main = tmem_base + (uint32_t)s * 256u;
+    const uint32_t x_lo = (smem_u32(bufs) >> 4) + (uint32_t)s * (kStkBuf >> 4) + kStkLead;       // centre row of chunk plane 0
+    constexpr uint32_t kStep = 2 * (kStkPlane >> 4);                                              // one k-step = two chunk planes
+    uint32_t wi = 0, wp = 0, opc = 0;
+    const long long t_begin = clock64();
+    long long t_dep = 0;
+    auto wait_dep = [&](bool first_of_read, int k) {
+      long long c0 = 0; if (p.prof) c0 = clock64();
+      mbar_wait(&sm->act_ready[s], opc & 1);
+      if (first_of_read) mbar_wait(&sm->in_full[s], (uint32_t)k & 1);
+      tc_fence_after();
+      if (p.prof) t_dep += clock64() - c0;
+    };
+    auto op_done = [&]() {
+      if (elect_one()) umma_commit(&sm->acc_full[s]);
+      __syncwarp();
+      ++opc;
+    };
+    auto stage_done = [&]() {
+      if (elect_one()) umma_commit(&wempty[wi]);
+      __syncwarp();
+      if (++wi == kStkStages) { wi = 0; wp ^= 1; }
+    };
+    for (int i = s, k = 0; i < n_reads; i += 2, ++k) {
+      for (int l = 0; l < p.num_layers; ++l) {
+        const StackLayer& L = p.layer[l];
+        const int residual = L.residual, highway = L.highway, ksteps = L.kc_in / 2, total = L.conv_blocks;
+        const uint32_t dil = (uint32_t)L.dil;
+        // ---- conv: D[cout][pos] = sum over taps and input-channel k-steps ----
+        wait_dep(l == 0, k);
+        if ((ksteps & 1) == 0) {
+          uint32_t acc = 0;
+          for (int tap = 0; tap < 3; ++tap) {
+            uint32_t bd_lo = (x_lo - dil + (uint32_t)tap * dil) | b_lbo_x;
+            for (int j = 0; j < ksteps; j += 2) {
+              mbar_wait(&wfull[wi], wp);
+              tc_fence_after();
+              const uint32_t a_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w;
               if (elect_one()) {
-                umma_bf16(d_main, a0d, bd, idesc_bott, k > 0);
-                umma_bf16(d_main + (uint32_t)p.bott, a1d, bd, idesc_bott, k > 0);
+                umma_bf16(d_main, stk_desc(a_lo, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, acc);
+                umma_bf16(d_main, stk_desc(a_lo + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
+              }
+              __syncwarp();
+              acc = 1;
+              bd_lo += 2 * kStep;
+              stage_done();
+            }
+          }
+        } else {
+          uint32_t bd_lo = x_lo - dil;
+          int jj = 0;
+          for (int blk = 0; blk < total; blk += 2) {
+            mbar_wait(&wfull[wi], wp);
+            tc_fence_after();
+            const uint32_t a_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w;
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+              if (blk + u < total) {
+                if (elect_one()) umma_bf16(d_main, stk_desc(a_lo + u * 256u, desc_hi), stk_desc(bd_lo | b_lbo_x, desc_hi), idesc_main, (blk + u) > 0);
+                __syncwarp();
+                bd_lo += kStep;
+                if (++jj == ksteps) { jj = 0; bd_lo += dil - (uint32_t)ksteps * kStep; }
               }
             }
-            __syncwarp();
-          }
-          if (elect_one()) umma_commit(&sm->w_empty[s][widx[s]]);
-          __syncwarp();
-          ++wc[s];
-          if (++widx[s] == kStkStages) widx[s] = 0;
-          blk[s] += nb;
-          if (p.prof) { t_issue += clock64() - t_i0; ++n_issue; }
-          if (blk[s] == total) {
-            if (elect_one()) umma_commit(&sm->acc_full[s]);
-            __syncwarp();
-            ++opc[s]; started[s] = false; blk[s] = 0; tap[s] = 0; jj[s] = 0;
-            int nk = -1;
-            if (kind[s] == 0) nk = L.residual ? 1 : (L.highway ? 2 : -1);
-            else if (kind[s] == 1) nk = L.highway ? 2 : -1;
-            if (nk >= 0) kind[s] = nk;
-            else {
-              kind[s] = 0;
-              if (++ly[s] == p.num_layers) { ly[s] = 0; rd[s] += 2; if (rd[s] >= n_reads) active[s] = false; }
-            }
+            stage_done();
           }
         }
-        if (p.prof) { const long long now = clock64(); if (!progressed) t_idle += now - t_mark; t_mark = now; }
-        if (progressed) idle = 0;
-        else if (++idle > (1u << 27)) __trap();     // a protocol bug must fail the launch, not hang the GPU
+        op_done();
+        // ---- residual 1x1: accumulates on x + b_res stored by the epilogue ----
+        if (residual) {
+          wait_dep(false, 0);
+          uint32_t bd_lo = x_lo | b_lbo_x;
+          for (int blk = 0; blk < kKC / 2; blk += 2) {
+            mbar_wait(&wfull[wi], wp);
+            tc_fence_after();
+            const uint32_t a_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w;
+            if (elect_one()) {
+              umma_bf16(d_main, stk_desc(a_lo, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, 1);
+              umma_bf16(d_main, stk_desc(a_lo + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
+            }
+            __syncwarp();
+            bd_lo += 2 * kStep;
+            stage_done();
+          }
+          op_done();
+        }
+        // ---- bottleneck 1x1, positions-as-M orientation: A = activation rows (two 128-row tiles), B = weights ----
+        if (highway) {
+          wait_dep(false, 0);
+          uint32_t xa_lo = x_lo | b_lbo_x;
+          for (int blk = 0; blk < kKC / 2; blk += bott_per_stage) {
+            mbar_wait(&wfull[wi], wp);
+            tc_fence_after();
+            uint32_t w_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | b_lbo_bott;
+            for (int u = 0; u < bott_per_stage; ++u) {
+              if (elect_one()) {
+                umma_bf16(d_main, stk_desc(xa_lo, desc_hi), stk_desc(w_lo, desc_hi), idesc_bott, (blk + u) > 0);
+                umma_bf16(d_main + (uint32_t)p.bott, stk_desc(xa_lo + 128u, desc_hi), stk_desc(w_lo, desc_hi), idesc_bott, (blk + u) > 0);
+              }
+              __syncwarp();
+              xa_lo += kStep;
+              w_lo += (uint32_t)p.bott * 2u;
+            }
+            stage_done();
+          }
+          op_done();
+        }
       }
-      if (p.prof && lane == 0) { p.prof[blockIdx.x * 12 + 0] = clock64() - t_begin; p.prof[blockIdx.x * 12 + 1] = t_idle; p.prof[blockIdx.x * 12 + 8] = t_issue; p.prof[blockIdx.x * 12 + 9] = n_issue; }
     }
+    if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 0 + 10 * s] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 1 + 10 * s] = t_dep; }
   } else {
-    // ===================== epilogue warpgroups =======================================================================
+    // ===================== epilogue warpgroups (slot s); thread 0 of the group also moves the slot's reads in and out ==
     const int s = warp >> 2, q = warp & 3;
+    const int gtid = threadIdx.x & 127;
     const uint32_t tbase = tmem_base + (uint32_t)s * 256u + ((uint32_t)(32 * q) << 16);
+    const uint32_t buf_addr = smem_u32(bufs + (size_t)s * kStkBuf);
+    if (gtid == 0 && s < n_reads) load_read(s);
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
     uint32_t opc = 0;
-    long long t_wait = 0, t_main = 0, t_bott = 0, t0 = 0;
-    const bool prof = p.prof != nullptr && (threadIdx.x & 127) == 0;
+    long long t_wait = 0, t_main = 0, t_bott = 0, t_io = 0, t0 = 0;
+    const bool prof = p.prof != nullptr && gtid == 0;
     for (int i = s; i < n_reads; i += 2) {
-      const int b = i % kStkNumBuf;
-      const uint32_t buf_addr = smem_u32(bufs + (size_t)b * kStkBuf);
       for (int l = 0; l < p.num_layers; ++l) {
         const StackLayer& L = p.layer[l];
         float bias[4], scale[4], shift[4], rbias[4];
@@ -321,12 +350,14 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         mbar_wait(&sm->acc_full[s], opc & 1);
         tc_fence_after();
         if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+        if (gtid == 0) stk_trace(p, 0x400u + (s << 6));
         if (L.residual) stack_epi_main<kEpiPreRes>(tbase, buf_addr, q, lane, p.P, bias, scale, shift, rbias);
         else stack_epi_main<kEpiFinal>(tbase, buf_addr, q, lane, p.P, bias, scale, shift, rbias);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&sm->act_ready[s]);
         ++opc;
+        if (gtid == 0) stk_trace(p, 0x500u + (s << 6));
         if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
         if (L.residual) {
           mbar_wait(&sm->acc_full[s], opc & 1);
@@ -339,6 +370,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           ++opc;
           if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
         }
+        const bool last = l + 1 == p.num_layers;
         if (L.highway) {
           mbar_wait(&sm->acc_full[s], opc & 1);
           tc_fence_after();
@@ -366,14 +398,29 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             }
           }
           tc_fence_before();
-          mbar_arrive(&sm->act_ready[s]);
+          if (!last) mbar_arrive(&sm->act_ready[s]);
           ++opc;
           if (prof) { const long long t1 = clock64(); t_bott += t1 - t0; t0 = t1; }
         }
+        if (last) {
+          // every MMA and epilogue of this read is done: store the segment output, refill the slot, then release the slot
+          // (when the layer has no bottleneck op the release above already happened: pull it back by waiting here instead)
+          named_bar_sync(1 + s, 128);
+          if (gtid == 0) {
+            uint4* dst = p.out + kLead + (long)(r_begin + i) * p.pitch;
+            const uint8_t* src = bufs + (size_t)s * kStkBuf + kStkLead * 16;
+            for (int kc = 0; kc < kKC; ++kc) bulk_s2g(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in);
+            bulk_commit();
+            bulk_wait_read0();
+            if (i + 2 < n_reads) load_read(i + 2);
+          }
+          if (L.highway) mbar_arrive(&sm->act_ready[s]);
+          if (prof) { const long long t1 = clock64(); t_io += t1 - t0; t0 = t1; }
+        }
       }
-      mbar_arrive(&sm->out_ready[b]);       // every MMA and epilogue of this read is done: the buffer may be stored and refilled
     }
-    if (prof) { unsigned long long* d = p.prof + blockIdx.x * 12 + 2 + 3 * s; d[0] = t_wait; d[1] = t_main; d[2] = t_bott; }
+    if (gtid == 0) bulk_wait0();
+    if (prof) { unsigned long long* d = p.prof + blockIdx.x * 16 + 2 + 3 * s; d[0] = t_wait; d[1] = t_main; d[2] = t_bott; p.prof[blockIdx.x * 16 + 8 + s] = t_io; }
   }
   tc_fence_before();
   __syncthreads();
