@@ -27,7 +27,8 @@
 
 namespace {
 
-constexpr int kStkThreads = 384;       // warps 0-3 epilogue slot 0 | 4-7 epilogue slot 1 | 8,9 weight producers | 10,11 MMA issuers
+constexpr int kStkThreads = 640;       // warps 0-7 epilogue slot 0 | 8-15 epilogue slot 1 | 16,17 weight producers | 18,19 MMA issuers
+constexpr int kStkEpiThreads = 256;    // epilogue threads per slot: 4 TMEM lane quadrants x 2 position halves
 constexpr int kStkLead = 2;            // zero rows in front of position 0 (>= largest dilation)
 constexpr int kStkN = 208;             // MMA N = positions per read, padded to a multiple of 16
 constexpr int kStkRB = kStkLead + kStkN + 2;   // rows per channel-chunk plane of a read buffer (212)
@@ -36,8 +37,8 @@ constexpr int kStkBuf = kKC * kStkPlane;       // bytes per read buffer (54272)
 constexpr int kStkStageBytes = 8192;   // weight-ring stage = two k-step blocks of 4 KB
 constexpr int kStkStages = 7;          // stages per slot
 constexpr int kStkMaxSeg = 8;          // layers per segment
-constexpr int kStkSmemHeader = 1024;
-constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + 2 * kStkStages * kStkStageBytes + 1024;   // + slack read by the bottleneck A tiles
+constexpr int kStkSmemHeader = 3072;   // barriers, TMEM pointer, bottleneck biases of the segment
+constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + 2 * kStkStages * kStkStageBytes;
 
 struct StackLayer {
   const uint8_t* wstream;   // conv k-step blocks (tap-major) | residual blocks | bottleneck blocks, contiguous
@@ -65,37 +66,47 @@ struct StackSmem {
   uint64_t w_full[2][kStkStages], w_empty[2][kStkStages];
   uint64_t acc_full[2], act_ready[2], in_full[2];
   uint32_t tmem_base;
+  float bbias[kStkMaxSeg][64];
 };
+static_assert(sizeof(StackSmem) <= kStkSmemHeader, "header too small");
 
 enum { kEpiFinal = 0, kEpiPreRes = 1, kEpiPostRes = 2 };
 
-// main-accumulator epilogue for one group of NG*8 positions starting at group g0 (see header comment)
-template <int NG, int MODE>
-__device__ __forceinline__ void stack_epi_chunk(uint32_t tbase, uint32_t buf_addr, int g0, int q, int lane, int P,
-                                                const float (&bias)[4], const float (&scale)[4], const float (&shift)[4],
-                                                const float (&rbias)[4]) {
-  uint32_t r0[4 * NG], r1[4 * NG];
-  if constexpr (NG == 4) { tmem_ld_16x256b_x4(tbase + g0 * 8, r0); tmem_ld_16x256b_x4(tbase + (16u << 16) + g0 * 8, r1); }
-  else { tmem_ld_16x256b_x2(tbase + g0 * 8, r0); tmem_ld_16x256b_x2(tbase + (16u << 16) + g0 * 8, r1); }
-  tmem_ld_wait();
-  uint32_t x0[4 * NG], x1[4 * NG];
+// ---- main-accumulator epilogue (see header comment). A warp owns TMEM lane quadrant q (channels 32q..32q+31) and a
+// range of 8-position groups; it walks the range in chunks of two groups (16 positions) with the TMEM load of the
+// next chunk in flight while the current one is converted and written. ----
+// y = s*relu(z + b) + t (ReLU then BatchNorm, model.py:749-751) is evaluated as one FFMA and one predicated min/max:
+//   s >= 0: max(s*z + c, t),  s < 0: min(s*z + c, t),  c = s*b + t
+struct EpiConsts { float scale[4], c[4], shift[4], rbias[4]; bool pos[4]; };
+
+__device__ __forceinline__ void stack_epi_load(uint32_t tbase, int g0, uint32_t (&r0)[8], uint32_t (&r1)[8]) {
+  tmem_ld_16x256b_x2(tbase + g0 * 8, r0);
+  tmem_ld_16x256b_x2(tbase + (16u << 16) + g0 * 8, r1);
+}
+
+template <int MODE, bool MASK>
+__device__ __forceinline__ void stack_epi_chunk(const uint32_t (&r0)[8], const uint32_t (&r1)[8], uint32_t tbase, uint32_t saddr0, int g0, int lane,
+                                                int P, const EpiConsts& k) {
+  uint32_t x0[8], x1[8];
 #pragma unroll
-  for (int gi = 0; gi < NG; ++gi) {
-    const int g = g0 + gi;
-    const int pos = 8 * g + 2 * (lane & 3);
-    const bool ok0 = pos < P, ok1 = pos + 1 < P;
-    // this thread's row of the four 8x8 blocks (channel chunks 4q..4q+3) of position group g
-    const uint32_t saddr = buf_addr + (uint32_t)(4 * q + (lane >> 3)) * kStkPlane + (uint32_t)(kStkLead + 8 * g + (lane & 7)) * 16;
+  for (int gi = 0; gi < 2; ++gi) {
+    // this thread's row of the four 8x8 blocks (channel chunks 4q..4q+3) of position group g0+gi
+    const uint32_t saddr = saddr0 + (uint32_t)(g0 + gi) * 128u;
     uint32_t pk[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t* src = (j < 2) ? r0 : r1;
       float lo = __uint_as_float(src[4 * gi + 2 * (j & 1)]), hi = __uint_as_float(src[4 * gi + 2 * (j & 1) + 1]);
       if constexpr (MODE != kEpiPostRes) {
-        lo = fmaf(fmaxf(lo + bias[j], 0.f), scale[j], shift[j]);      // ReLU, then BatchNorm (model.py:749-751)
-        hi = fmaf(fmaxf(hi + bias[j], 0.f), scale[j], shift[j]);
+        lo = fmaf(lo, k.scale[j], k.c[j]); hi = fmaf(hi, k.scale[j], k.c[j]);
+        lo = k.pos[j] ? fmaxf(lo, k.shift[j]) : fminf(lo, k.shift[j]);
+        hi = k.pos[j] ? fmaxf(hi, k.shift[j]) : fminf(hi, k.shift[j]);
       }
-      pk[j] = pack_bf16x2(ok0 ? lo : 0.f, ok1 ? hi : 0.f);
+      if constexpr (MASK) {                                                   // positions >= P are the zero rows behind the read
+        const int pos = 8 * (g0 + gi) + 2 * (lane & 3);
+        lo = pos < P ? lo : 0.f; hi = pos + 1 < P ? hi : 0.f;
+      }
+      pk[j] = pack_bf16x2(lo, hi);
     }
     if constexpr (MODE == kEpiPreRes) {
       uint32_t xin[4];
@@ -103,24 +114,29 @@ __device__ __forceinline__ void stack_epi_chunk(uint32_t tbase, uint32_t buf_add
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         uint32_t* dst = (j < 2) ? x0 : x1;
-        dst[4 * gi + 2 * (j & 1)] = __float_as_uint(bf16_lo(xin[j]) + rbias[j]);
-        dst[4 * gi + 2 * (j & 1) + 1] = __float_as_uint(bf16_hi(xin[j]) + rbias[j]);
+        dst[4 * gi + 2 * (j & 1)] = __float_as_uint(bf16_lo(xin[j]) + k.rbias[j]);
+        dst[4 * gi + 2 * (j & 1) + 1] = __float_as_uint(bf16_hi(xin[j]) + k.rbias[j]);
       }
     }
     stmatrix_x4_trans(saddr, pk[0], pk[1], pk[2], pk[3]);
   }
   if constexpr (MODE == kEpiPreRes) {     // accumulator := x + b_res; the residual 1x1 MMA accumulates on top (model.py:760-761)
-    if constexpr (NG == 4) { tmem_st_16x256b_x4(tbase + g0 * 8, x0); tmem_st_16x256b_x4(tbase + (16u << 16) + g0 * 8, x1); }
-    else { tmem_st_16x256b_x2(tbase + g0 * 8, x0); tmem_st_16x256b_x2(tbase + (16u << 16) + g0 * 8, x1); }
+    tmem_st_16x256b_x2(tbase + g0 * 8, x0);
+    tmem_st_16x256b_x2(tbase + (16u << 16) + g0 * 8, x1);
   }
 }
 
+// groups [g_begin, g_end), (g_end - g_begin) a multiple of 2; the chunk containing group 25 masks positions >= P
 template <int MODE>
-__device__ __forceinline__ void stack_epi_main(uint32_t tbase, uint32_t buf_addr, int q, int lane, int P, const float (&bias)[4],
-                                               const float (&scale)[4], const float (&shift)[4], const float (&rbias)[4]) {
+__device__ __forceinline__ void stack_epi_main(uint32_t tbase, uint32_t saddr0, int lane, int P, int g_begin, int g_end, const EpiConsts& k) {
 #pragma unroll 1
-  for (int g0 = 0; g0 < 24; g0 += 4) stack_epi_chunk<4, MODE>(tbase, buf_addr, g0, q, lane, P, bias, scale, shift, rbias);
-  stack_epi_chunk<2, MODE>(tbase, buf_addr, 24, q, lane, P, bias, scale, shift, rbias);
+  for (int g0 = g_begin; g0 < g_end; g0 += 2) {
+    uint32_t a0[8], a1[8];
+    stack_epi_load(tbase, g0, a0, a1);
+    tmem_ld_wait();
+    if (g0 == 24) stack_epi_chunk<MODE, true>(a0, a1, tbase, saddr0, g0, lane, P, k);
+    else stack_epi_chunk<MODE, false>(a0, a1, tbase, saddr0, g0, lane, P, k);
+  }
   if constexpr (MODE == kEpiPreRes) tmem_st_wait();
 }
 
@@ -154,12 +170,16 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) {
       for (int i = 0; i < kStkStages; ++i) { mbar_init(&sm->w_full[s][i], 1); mbar_init(&sm->w_empty[s][i], 1); }
-      mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], 128); mbar_init(&sm->in_full[s], 1);
+      mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], kStkEpiThreads); mbar_init(&sm->in_full[s], 1);
     }
     fence_mbar_init();
   }
+  for (int i = threadIdx.x; i < p.num_layers * 64; i += kStkThreads) {
+    const int l = i >> 6, c = i & 63;
+    sm->bbias[l][c] = (p.layer[l].highway && c < p.bott) ? p.layer[l].bbias[c] : 0.f;
+  }
   fence_proxy_async_smem();
-  if (warp == 10) tmem_alloc<512>(&sm->tmem_base);
+  if (warp == 18) tmem_alloc<512>(&sm->tmem_base);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -174,10 +194,10 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     for (int kc = 0; kc < in_kc; ++kc) bulk_g2s(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s]);
   };
 
-  if (warp == 8 || warp == 9) {
+  if (warp == 16 || warp == 17) {
     // ===================== weight producer of slot s: streams every op's A/B blocks in issue order =================
     if (lane == 0) {
-      const int s = warp - 8;
+      const int s = warp - 16;
       uint8_t* ring = rings + (size_t)s * kStkStages * kStkStageBytes;
       uint32_t idx = 0, par = 1;     // first pass over the ring: the "empty" phase counts as complete
       auto emit = [&](const uint8_t* src, uint32_t bytes) {
@@ -200,14 +220,14 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 10 || warp == 11) {
+  } else if (warp == 18 || warp == 19) {
     // ===================== MMA issuer of slot s. The whole warp runs the (blocking, strictly sequential) op schedule of
     // its slot — warp-uniform control flow keeps descriptors in uniform registers — and one elected lane issues the
     // tcgen05 instructions. The two slots' issuers are independent warps: the tensor pipe interleaves their MMA
     // streams, so one slot's epilogue runs under the other slot's MMAs without any software multiplexing. A single
     // warp retires one dependent instruction every ~4 cycles, so the loops below are kept to a few instructions
     // per MMA (descriptor words are advanced by constants). =========================================================
-    const int s = warp - 10;
+    const int s = warp - 18;
     const uint32_t idesc_main = make_idesc_bf16(128, kStkN);
     const uint32_t idesc_bott = make_idesc_bf16(128, p.bott);
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
@@ -327,11 +347,15 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     }
     if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 0 + 10 * s] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 1 + 10 * s] = t_dep; }
   } else {
-    // ===================== epilogue warpgroups (slot s); thread 0 of the group also moves the slot's reads in and out ==
-    const int s = warp >> 2, q = warp & 3;
-    const int gtid = threadIdx.x & 127;
+    // ===================== epilogue warps of slot s: quadrant q = TMEM lanes / channels 32q.., half h = position range;
+    // thread 0 of the slot's group also moves the slot's reads in and out ==========================================
+    const int s = warp >> 3, h = (warp >> 2) & 1, q = warp & 3;
+    const int gtid = threadIdx.x & (kStkEpiThreads - 1);
     const uint32_t tbase = tmem_base + (uint32_t)s * 256u + ((uint32_t)(32 * q) << 16);
     const uint32_t buf_addr = smem_u32(bufs + (size_t)s * kStkBuf);
+    // stmatrix / ldmatrix row address of this thread for position group 0: matrix lane>>3 = chunk plane 4q + (lane>>3), row lane&7
+    const uint32_t saddr0 = buf_addr + (uint32_t)(4 * q + (lane >> 3)) * kStkPlane + (uint32_t)(kStkLead + (lane & 7)) * 16;
+    const int g_begin = h == 0 ? 0 : 14, g_end = h == 0 ? 14 : 26;
     if (gtid == 0 && s < n_reads) load_read(s);
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
     uint32_t opc = 0;
@@ -340,30 +364,30 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     for (int i = s; i < n_reads; i += 2) {
       for (int l = 0; l < p.num_layers; ++l) {
         const StackLayer& L = p.layer[l];
-        float bias[4], scale[4], shift[4], rbias[4];
+        EpiConsts k;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = 32 * q + 8 * j + (lane >> 2);
-          bias[j] = __ldg(L.chan + c); scale[j] = __ldg(L.chan + kC + c); shift[j] = __ldg(L.chan + 2 * kC + c); rbias[j] = __ldg(L.chan + 3 * kC + c);
+          const float b = __ldg(L.chan + c);
+          k.scale[j] = __ldg(L.chan + kC + c); k.shift[j] = __ldg(L.chan + 2 * kC + c); k.rbias[j] = __ldg(L.chan + 3 * kC + c);
+          k.c[j] = fmaf(k.scale[j], b, k.shift[j]); k.pos[j] = k.scale[j] >= 0.f;
         }
         if (prof) t0 = clock64();
         mbar_wait(&sm->acc_full[s], opc & 1);
         tc_fence_after();
         if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-        if (gtid == 0) stk_trace(p, 0x400u + (s << 6));
-        if (L.residual) stack_epi_main<kEpiPreRes>(tbase, buf_addr, q, lane, p.P, bias, scale, shift, rbias);
-        else stack_epi_main<kEpiFinal>(tbase, buf_addr, q, lane, p.P, bias, scale, shift, rbias);
+        if (L.residual) stack_epi_main<kEpiPreRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
+        else stack_epi_main<kEpiFinal>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
         fence_proxy_async_smem();
         tc_fence_before();
         mbar_arrive(&sm->act_ready[s]);
         ++opc;
-        if (gtid == 0) stk_trace(p, 0x500u + (s << 6));
         if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
         if (L.residual) {
           mbar_wait(&sm->acc_full[s], opc & 1);
           tc_fence_after();
           if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-          stack_epi_main<kEpiPostRes>(tbase, buf_addr, q, lane, p.P, bias, scale, shift, rbias);
+          stack_epi_main<kEpiPostRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(&sm->act_ready[s]);
@@ -375,25 +399,23 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           mbar_wait(&sm->acc_full[s], opc & 1);
           tc_fence_after();
           if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+          // bottleneck tile h: TMEM lane = position 128h + 32q + lane, columns = bottleneck channels
           const int c8n = p.bott / 8;
-          for (int tile = 0; tile < 2; ++tile) {
-            const int pos = 128 * tile + 32 * q + lane;
-            for (int cc = 0; cc < p.bott / 32; ++cc) {
-              uint32_t r[32];
-              tmem_ld32(tbase + (uint32_t)(tile * p.bott + cc * 32), r);
-              tmem_ld_wait();
-              if (pos < p.P) {
+          const int pos = 128 * h + 32 * q + lane;
+          for (int cc = 0; cc < p.bott / 32; ++cc) {
+            uint32_t r[32];
+            tmem_ld32(tbase + (uint32_t)(h * p.bott + cc * 32), r);
+            tmem_ld_wait();
+            if (pos < p.P) {
+              const float* bb = &sm->bbias[l][cc * 32];
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                  const float4 b0 = __ldg(reinterpret_cast<const float4*>(L.bbias + cc * 32 + g * 8));
-                  const float4 b1 = __ldg(reinterpret_cast<const float4*>(L.bbias + cc * 32 + g * 8 + 4));
-                  uint4 o;                                                                 // relu(bottleneck), model.py:774
-                  o.x = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 0]) + b0.x, 0.f), fmaxf(__uint_as_float(r[g * 8 + 1]) + b0.y, 0.f));
-                  o.y = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 2]) + b0.z, 0.f), fmaxf(__uint_as_float(r[g * 8 + 3]) + b0.w, 0.f));
-                  o.z = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 4]) + b1.x, 0.f), fmaxf(__uint_as_float(r[g * 8 + 5]) + b1.y, 0.f));
-                  o.w = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 6]) + b1.z, 0.f), fmaxf(__uint_as_float(r[g * 8 + 7]) + b1.w, 0.f));
-                  L.tout[((long)pos * c8n + cc * 4 + g) * p.t_reads_stride + (r_begin + i)] = o;
-                }
+              for (int g = 0; g < 4; ++g) {
+                uint4 o;                                                                 // relu(bottleneck), model.py:774
+                o.x = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 0]) + bb[g * 8 + 0], 0.f), fmaxf(__uint_as_float(r[g * 8 + 1]) + bb[g * 8 + 1], 0.f));
+                o.y = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 2]) + bb[g * 8 + 2], 0.f), fmaxf(__uint_as_float(r[g * 8 + 3]) + bb[g * 8 + 3], 0.f));
+                o.z = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 4]) + bb[g * 8 + 4], 0.f), fmaxf(__uint_as_float(r[g * 8 + 5]) + bb[g * 8 + 5], 0.f));
+                o.w = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 6]) + bb[g * 8 + 6], 0.f), fmaxf(__uint_as_float(r[g * 8 + 7]) + bb[g * 8 + 7], 0.f));
+                L.tout[((long)pos * c8n + cc * 4 + g) * p.t_reads_stride + (r_begin + i)] = o;
               }
             }
           }
@@ -403,9 +425,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           if (prof) { const long long t1 = clock64(); t_bott += t1 - t0; t0 = t1; }
         }
         if (last) {
-          // every MMA and epilogue of this read is done: store the segment output, refill the slot, then release the slot
-          // (when the layer has no bottleneck op the release above already happened: pull it back by waiting here instead)
-          named_bar_sync(1 + s, 128);
+          // every MMA and epilogue of this read is done: store the segment output and refill the slot before releasing it
+          named_bar_sync(1 + s, kStkEpiThreads);
           if (gtid == 0) {
             uint4* dst = p.out + kLead + (long)(r_begin + i) * p.pitch;
             const uint8_t* src = bufs + (size_t)s * kStkBuf + kStkLead * 16;
@@ -424,7 +445,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 10) tmem_dealloc<512>(tmem_base);
+  if (warp == 18) tmem_dealloc<512>(tmem_base);
 }
 
 }  // namespace
