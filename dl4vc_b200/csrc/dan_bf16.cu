@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) dan_layer_kernel(const __gri
               for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(r[g * 8 + j]) + p.bbias[c * 32 + g * 8 + j], 0.f);   // model.py:774
               uint4 o;
               o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-              p.tout[((long)pp * (p.bott / 8) + c * 4 + g) * p.t_reads_stride + read] = o;
+              p.tout[((long)read * p.P + pp) * (p.bott / 8) + c * 4 + g] = o;
             }
           }
         }
@@ -389,121 +389,9 @@ __global__ void __launch_bounds__(kLayerThreads, 1) dan_layer_kernel(const __gri
   if (warp == 9) tmem_dealloc<512>(tmem_base);
 }
 
-// =====================================================================================================
-// Streaming split-K GEMM:  out[M][N] (+)= A[M][K] * B[N][K]^T, both operands chunk-major (16-byte pieces)
-// =====================================================================================================
-constexpr int kGemmThreads = 192;     // warp 0 producer, warp 1 MMA issuer, warps 2-5 epilogue
-constexpr int kStageKC = 8;           // 8 pieces = 64 K elements per stage
-
-struct GemmParams {
-  const uint4* A; long a_kstride;
-  const uint4* B; long b_kstride;
-  int M, N, KC;                       // KC = K/8 (even)
-  int m_tiles, n_tiles, splits;
-  float* out; int ldo;
-};
-
-template <int BN>
-__host__ __device__ constexpr int gemm_stages() { return BN == 128 ? 6 : 8; }
-template <int BN>
-__host__ __device__ constexpr size_t gemm_smem_bytes() { return 1024 + (size_t)gemm_stages<BN>() * kStageKC * (128 + BN) * 16; }
-
-template <int BN>
-__global__ void __launch_bounds__(kGemmThreads, 1) stream_gemm_kernel(const __grid_constant__ GemmParams p) {
-  constexpr int NS = gemm_stages<BN>();
-  constexpr uint32_t kABytes = kStageKC * 128 * 16, kBBytes = kStageKC * BN * 16;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  uint64_t* full = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* empty = full + NS;
-  uint64_t* done = empty + NS;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(done + 1);
-  uint8_t* stage_base = smem + 1024;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  int w = blockIdx.x;
-  const int m_tile = w % p.m_tiles; w /= p.m_tiles;
-  const int n_tile = w % p.n_tiles; w /= p.n_tiles;
-  const int split = w;
-  const int total_stages = (p.KC + kStageKC - 1) / kStageKC;
-  const int per = (total_stages + p.splits - 1) / p.splits;
-  const int st_begin = split * per, st_end = min(total_stages, st_begin + per);
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < NS; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
-    mbar_init(done, 1);
-    fence_mbar_init();
-  }
-  if (warp == 1) tmem_alloc<BN < 32 ? 32 : BN>(tmem_ptr);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-
-  if (st_begin < st_end) {
-    if (warp == 0) {
-      if (lane == 0) {
-        for (int st = st_begin; st < st_end; ++st) {
-          const int i = (st - st_begin) % NS, round = (st - st_begin) / NS;
-          mbar_wait(&empty[i], (round & 1) ^ 1);
-          const int kc0 = st * kStageKC, nkc = min(kStageKC, p.KC - kc0);
-          mbar_expect_tx(&full[i], (uint32_t)nkc * (128 + BN) * 16);
-          uint8_t* a_dst = stage_base + (size_t)i * (kABytes + kBBytes);
-          uint8_t* b_dst = a_dst + kABytes;
-          for (int k = 0; k < nkc; ++k) {
-            bulk_g2s(a_dst + k * 128 * 16, p.A + (long)(kc0 + k) * p.a_kstride + (long)m_tile * 128, 128 * 16, &full[i]);
-            bulk_g2s(b_dst + k * BN * 16, p.B + (long)(kc0 + k) * p.b_kstride + (long)n_tile * BN, BN * 16, &full[i]);
-          }
-        }
-      }
-    } else if (warp == 1) {
-      if (lane == 0) {
-        const uint32_t idesc = make_idesc_bf16(128, BN);
-        uint32_t acc = 0;
-        for (int st = st_begin; st < st_end; ++st) {
-          const int i = (st - st_begin) % NS, round = (st - st_begin) / NS;
-          mbar_wait(&full[i], round & 1);
-          tc_fence_after();
-          const int kc0 = st * kStageKC, nkc = min(kStageKC, p.KC - kc0);
-          const uint32_t a0 = smem_u32(stage_base + (size_t)i * (kABytes + kBBytes)), b0 = a0 + kABytes;
-          for (int k2 = 0; k2 < nkc; k2 += 2) {
-            umma_bf16(tmem_base, make_smem_desc(a0 + k2 * (128 * 16), 128 * 16, 128), make_smem_desc(b0 + k2 * (BN * 16), BN * 16, 128), idesc, acc);
-            acc = 1;
-          }
-          umma_commit(&empty[i]);
-        }
-        umma_commit(done);
-      }
-    } else {
-      const int q = warp & 3;
-      const int row = m_tile * 128 + q * 32 + lane;
-      mbar_wait(done, 0);
-      tc_fence_after();
-      float* orow = p.out + (long)row * p.ldo + (long)n_tile * BN;
-#pragma unroll
-      for (int c = 0; c < BN / 32; ++c) {
-        uint32_t r[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + c * 32, r);
-        tmem_ld_wait();
-        if (row < p.M) {
-          if (p.splits > 1) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) atomicAdd(orow + c * 32 + j, __uint_as_float(r[j]));
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; j += 4)
-              *reinterpret_cast<float4*>(orow + c * 32 + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-          }
-        }
-      }
-      tc_fence_before();
-    }
-  }
-  __syncthreads();
-  if (warp == 1) tmem_dealloc<BN < 32 ? 32 : BN>(tmem_base);
-}
-
 }  // namespace
 #include "dan_stack.cuh"
+#include "dan_gemm.cuh"
 namespace {
 
 // =====================================================================================================
@@ -573,12 +461,12 @@ __global__ void pool_final_bf16_kernel(const uint4* __restrict__ h, long kstride
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) s[j] /= (float)g.R;
-  const long col = cand0 + cand;
+  uint4* row = fcin + (long)(cand0 + cand) * fc_kstride;          // fc_kstride = pieces per FC-input row
   if (skip_max) {
-    fcin[((long)pp * kKC + kc) * fc_kstride + col] = pack8(s);
+    row[(long)pp * kKC + kc] = pack8(s);
   } else {
-    fcin[((long)pp * kKC + kc) * fc_kstride + col] = pack8(mx);
-    fcin[((long)(g.P + pp) * kKC + kc) * fc_kstride + col] = pack8(s);
+    row[(long)pp * kKC + kc] = pack8(mx);
+    row[(long)(g.P + pp) * kKC + kc] = pack8(s);
   }
 }
 
@@ -608,30 +496,7 @@ __global__ void highway_finish_bf16_kernel(const float* __restrict__ hw, long la
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j] / (float)L, 0.f);
     }
-    fcin[(base_kc + ((long)l * R + r) * o8n + o8) * fc_kstride + cand0 + cand] = pack8(f);
-  }
-}
-
-// FC finish: partial fp32 [M][N] + bias -> relu -> bf16 pieces [N/8][kstride]
-__global__ void fc_finish_bf16_kernel(const float* __restrict__ part, int M, int N, const float* __restrict__ bias,
-                                      uint4* __restrict__ out, long kstride) {
-  const long total = (long)M * (N / 8);
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int m = (int)(i % M); const int kc = (int)(i / M);
-    float f[8];
-#pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = fmaxf(part[(long)m * N + kc * 8 + j] + bias[kc * 8 + j], 0.f);
-    out[kc * kstride + m] = pack8(f);
-  }
-}
-__global__ void heads_finish_kernel(const float* __restrict__ part, int M, const float* __restrict__ bias, float* __restrict__ out) {
-  const long total = (long)M * DAN_NUM_HEAD_OUTPUTS;
-  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
-    const int n = (int)(i % DAN_NUM_HEAD_OUTPUTS); const long m = i / DAN_NUM_HEAD_OUTPUTS;
-    float v = part[m * DAN_HEAD_PAD + n] + bias[n];
-    if (n == 5) v = 1.f / (1.f + expf(-v));
-    else if (n == 6) v = v >= 0.f ? v : 0.01f * v;
-    out[i] = v;
+    fcin[(long)(cand0 + cand) * fc_kstride + base_kc + ((long)l * R + r) * o8n + o8] = pack8(f);
   }
 }
 
@@ -652,7 +517,7 @@ __global__ void pack_conv_bf16_kernel(const float* __restrict__ w, uint4* __rest
     store_bf16(out, ((long)tap * kc_in + kc) * kC + n, j, c < Cin ? w[((long)n * Cin + c) * 3 + tap] : 0.f);
   }
 }
-// linear-like (N, K) fp32 with optional source-column map -> [kc][Npad][8]
+// linear-like (N, K) fp32 with optional source-column map -> bf16 row-major [Npad][Kpad] (mode 3: UMMA chunk image [kc][Npad][8])
 __global__ void pack_linear_bf16_kernel(const float* __restrict__ w, uint4* __restrict__ out, int N, int Npad, int K, int Kpad,
                                         int mode, int P, int C, int R, int bott, int L, int pooled, int skip_max) {
   // mode 0: identity columns. mode 1: FC1 feature permutation (see dan_bf16_forward). mode 2: compression (O, Cb, 1, P): k = p*bott + c
@@ -682,12 +547,14 @@ __global__ void pack_linear_bf16_kernel(const float* __restrict__ w, uint4* __re
       }
       v = w[(long)n * K + src];
     }
-    store_bf16(out, kc * Npad + n, j, v);
+    if (mode == 3) store_bf16(out, kc * Npad + n, j, v);
+    else reinterpret_cast<__nv_bfloat16*>(out)[(long)n * Kpad + k] = __float2bfloat16_rn(v);
   }
 }
 
 struct Bf16Weights {
   uint4* wconv[DAN_MAX_LAYERS]; uint4* wres[DAN_MAX_LAYERS]; uint4* wbott[DAN_MAX_LAYERS]; uint4* wcomp[DAN_MAX_LAYERS];
+  uint4* wcomp_all;                   // all layers' compression weights, [L][bott][P*bott] bf16 (one batched GEMM operand)
   uint4* fcw[DAN_MAX_FC]; uint4* headw;
   const float** comp_bias_ptrs;       // device array of L pointers
   uint8_t* wstream[DAN_MAX_LAYERS];   // conv | residual | bottleneck operand images of a layer, contiguous (dan_stack.cuh); kWeightReplicas copies
@@ -711,7 +578,7 @@ struct Bf16Plan {
   long hw_layer_stride;
   long t_layer_pieces;               // uint4 pieces of one layer's T matrix
   int fcKC;                          // FC input pieces
-  size_t off_zero_begin, off_x0, off_h[3], off_zero_end, off_t, off_pool, off_agree, off_hw, off_fcin, off_fcx[DAN_MAX_FC], off_part, total;
+  size_t off_zero_begin, off_x0, off_h[3], off_zero_end, off_t, off_pool, off_agree, off_hw, off_fcin, off_fcx[DAN_MAX_FC], total;
   int maxN;
 };
 
@@ -738,48 +605,14 @@ Bf16Plan make_plan(const dan_model* m, int batch) {
   pl.off_agree = take((size_t)pl.S * 2 * m->R);
   pl.hw_layer_stride = pl.readsPad * bott;
   pl.off_hw = take((size_t)m->L * pl.hw_layer_stride * 4);
-  pl.off_fcin = take((size_t)pl.fcKC * pl.BcPad * 16);
+  pl.off_fcin = take((size_t)pl.fcKC * pl.BcPad * 16);           // [BcPad][fcInPad] bf16, row-major
   pl.maxN = DAN_HEAD_PAD;
   for (int i = 0; i < m->cfg.num_fc; ++i) {
     pl.off_fcx[i] = take((size_t)(m->cfg.fc_sizes[i] / 8) * pl.BcPad * 16);
     if (m->cfg.fc_sizes[i] > pl.maxN) pl.maxN = m->cfg.fc_sizes[i];
   }
-  pl.off_part = take((size_t)pl.BcPad * pl.maxN * 4);
   pl.total = off;
   return pl;
-}
-
-template <int BN>
-int launch_gemm_bn(const GemmParams& g, cudaStream_t st) {
-  static thread_local bool attr = false;
-  if (!attr) {
-    DAN_CUDA_TRY(cudaFuncSetAttribute(stream_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem_bytes<BN>()));
-    attr = true;
-  }
-  { DanProfScope ps(DAN_PROF_GEMM, st); stream_gemm_kernel<BN><<<g.m_tiles * g.n_tiles * g.splits, kGemmThreads, gemm_smem_bytes<BN>(), st>>>(g); }
-  dan_count_launch();
-  DAN_CUDA_TRY(cudaGetLastError());
-  return DAN_OK;
-}
-
-// out (fp32, zeroed here when split) = A * B^T
-int run_gemm(const uint4* A, long a_kstride, const uint4* B, long b_kstride, int M, int N, int KC, float* out, int ldo,
-             int num_sms, cudaStream_t st) {
-  GemmParams g{};
-  g.A = A; g.a_kstride = a_kstride; g.B = B; g.b_kstride = b_kstride; g.M = M; g.N = N; g.KC = KC; g.out = out; g.ldo = ldo;
-  const int bn = N >= 128 ? 128 : 32;
-  g.m_tiles = (M + 127) / 128; g.n_tiles = N / bn;
-  const int total_stages = (KC + kStageKC - 1) / kStageKC;
-  int splits = 1;
-  const int base = g.m_tiles * g.n_tiles;
-  if (base < num_sms) splits = (num_sms + base - 1) / base;
-  if (splits > total_stages / 4) splits = total_stages / 4 > 0 ? total_stages / 4 : 1;
-  // avoid empty trailing splits
-  const int per = (total_stages + splits - 1) / splits;
-  splits = (total_stages + per - 1) / per;
-  g.splits = splits;
-  if (splits > 1) DAN_CUDA_TRY(cudaMemsetAsync(out, 0, (size_t)M * ldo * 4, st));
-  return bn == 128 ? launch_gemm_bn<128>(g, st) : launch_gemm_bn<32>(g, st);
 }
 
 }  // namespace
@@ -827,12 +660,13 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
     }
     pack_conv_bf16_kernel<<<grid_for((long)3 * kc_in * kC * 8), 256, 0, st>>>(w->conv_w[l], bw->wconv[l], cin, kc_in);
     if (m->cfg.is_residual[l]) {
-      pack_linear_bf16_kernel<<<grid_for((long)kKC * kC * 8), 256, 0, st>>>(w->res_w[l], bw->wres[l], kC, kC, kC, kC, 0, P, kC, R, bott, L, 0, 0);
+      pack_linear_bf16_kernel<<<grid_for((long)kKC * kC * 8), 256, 0, st>>>(w->res_w[l], bw->wres[l], kC, kC, kC, kC, 3, P, kC, R, bott, L, 0, 0);
     }
     if (m->cfg.highway) {
-      pack_linear_bf16_kernel<<<grid_for((long)kKC * bott * 8), 256, 0, st>>>(w->bott_w[l], bw->wbott[l], bott, bott, kC, kC, 0, P, kC, R, bott, L, 0, 0);
+      pack_linear_bf16_kernel<<<grid_for((long)kKC * bott * 8), 256, 0, st>>>(w->bott_w[l], bw->wbott[l], bott, bott, kC, kC, 3, P, kC, R, bott, L, 0, 0);
       const int K = P * bott;
-      if ((rc = alloc(&bw->wcomp[l], (size_t)(K / 8) * bott))) return rc;
+      if ((rc = alloc(&bw->wcomp_all, (size_t)L * (K / 8) * bott))) return rc;
+      bw->wcomp[l] = bw->wcomp_all + (size_t)l * (K / 8) * bott;
       pack_linear_bf16_kernel<<<grid_for((long)K * bott), 256, 0, st>>>(w->comp_w[l], bw->wcomp[l], bott, bott, K, K, 2, P, kC, R, bott, L, 0, 0);
     }
   }
@@ -881,7 +715,8 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
 void dan_bf16_free(dan_model* m) {
   Bf16Weights* bw = static_cast<Bf16Weights*>(m->bf16_store);
   if (!bw) return;
-  for (int l = 0; l < DAN_MAX_LAYERS; ++l) { cudaFree(bw->wstream[l]); cudaFree(bw->wcomp[l]); }
+  for (int l = 0; l < DAN_MAX_LAYERS; ++l) cudaFree(bw->wstream[l]);
+  cudaFree(bw->wcomp_all);
   cudaFree(bw->chan_dev);
   for (int i = 0; i < DAN_MAX_FC; ++i) cudaFree(bw->fcw[i]);
   cudaFree(bw->headw);
@@ -907,7 +742,16 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
                            encode_prod_smem_bytes(R) <= 48 * 1024;
   float* HW = reinterpret_cast<float*>(base + pl.off_hw);
   uint4* FCIN = reinterpret_cast<uint4*>(base + pl.off_fcin);
-  float* PART = reinterpret_cast<float*>(base + pl.off_part);
+  // highway compression (model.py:776) of every layer of a pass as ONE batched GEMM: HW[l][read][o] = T[l][read][:] . Wc[l][o][:]
+  auto run_compression = [&](int l0, int nl, int reads) -> int {
+    const long K = (long)P * bott;
+    Gemm2Operand A{T + (long)l0 * pl.t_layer_pieces, reads, K * 2, pl.t_layer_pieces * 16};
+    Gemm2Operand B{bw->wcomp[l0], bott, K * 2, K * 2 * bott};
+    Gemm2Params gp{};
+    gp.M = reads; gp.N = bott; gp.K = (int)K; gp.mode = kG2Raw;
+    gp.out = HW + (long)l0 * pl.hw_layer_stride; gp.out_batch_stride = pl.hw_layer_stride; gp.ldo = bott;
+    return run_gemm2(A, B, gp, nl, bw->num_sms, st);
+  };
   int rc;
 
   static thread_local bool attr_set = false;
@@ -1015,10 +859,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           l = l_end;
         }
         if (m->cfg.highway) {
-          for (int k = 0; k < L; ++k) {
-            rc = run_gemm(T + (long)k * pl.t_layer_pieces, pl.readsPad, bw->wcomp[k], bott, ns * R, bott, P * bott / 8, HW + (long)k * pl.hw_layer_stride, bott, bw->num_sms, st);
-            if (rc) return rc;
-          }
+          if ((rc = run_compression(0, L, ns * R))) return rc;
         }
       } else
       for (int l = 0; l < L; ++l) {
@@ -1052,39 +893,42 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           DAN_CUDA_TRY(cudaGetLastError());
         }
         if (m->cfg.highway) {
-          rc = run_gemm(T + (long)l * pl.t_layer_pieces, pl.readsPad, bw->wcomp[l], bott, ns * R, bott, P * bott / 8, HW + (long)l * pl.hw_layer_stride, bott, bw->num_sms, st);
-          if (rc) return rc;
+          if ((rc = run_compression(l, 1, ns * R))) return rc;
         }
         cur = next; hsel = (hsel + 1) % 3;
       }
-      { DanProfScope ps(DAN_PROF_POOL, st); pool_final_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(cur, pl.kstride, FCIN, pl.BcPad, s0, g, m->cfg.skip_final_maxpool); }
+      { DanProfScope ps(DAN_PROF_POOL, st); pool_final_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(cur, pl.kstride, FCIN, pl.fcKC, s0, g, m->cfg.skip_final_maxpool); }
       dan_count_launch();
       DAN_CUDA_TRY(cudaGetLastError());
       if (m->cfg.highway) {
         const int Lh = m->cfg.concat_hw_reads ? L : 1;
         { DanProfScope ps(DAN_PROF_POOL, st); highway_finish_bf16_kernel<<<grid_for((long)ns * Lh * R * (bott / 8)), 256, 0, st>>>(
-            HW, pl.hw_layer_stride, bw->comp_bias_ptrs, L, bott, R, m->cfg.concat_hw_reads, FCIN, pl.BcPad, m->pooled / 8, s0, ns); }
+            HW, pl.hw_layer_stride, bw->comp_bias_ptrs, L, bott, R, m->cfg.concat_hw_reads, FCIN, pl.fcKC, m->pooled / 8, s0, ns); }
         dan_count_launch();
         DAN_CUDA_TRY(cudaGetLastError());
       }
     }
     // ---- FC trunk + heads (model.py:917-958) ----
-    const uint4* x = FCIN; int KC = pl.fcKC;
+    const uint4* x = FCIN; int K = m->fcInPad;
     for (int i = 0; i < m->cfg.num_fc; ++i) {
       const int N = m->cfg.fc_sizes[i];
-      rc = run_gemm(x, pl.BcPad, bw->fcw[i], N, nb, N, KC, PART, N, bw->num_sms, st);
-      if (rc) return rc;
       uint4* y = reinterpret_cast<uint4*>(base + pl.off_fcx[i]);
-      { DanProfScope ps(DAN_PROF_POOL, st); fc_finish_bf16_kernel<<<grid_for((long)nb * (N / 8)), 256, 0, st>>>(PART, nb, N, m->fcB[i], y, pl.BcPad); }
-      dan_count_launch();
-      DAN_CUDA_TRY(cudaGetLastError());
-      x = y; KC = N / 8;
+      Gemm2Operand A{x, nb, (long)K * 2, 0};
+      Gemm2Operand B{bw->fcw[i], N, (long)K * 2, 0};
+      Gemm2Params gp{};
+      gp.M = nb; gp.N = N; gp.K = K; gp.mode = kG2BiasReluBf16; gp.bias = m->fcB[i];
+      gp.out_bf16 = reinterpret_cast<__nv_bfloat16*>(y); gp.ld_bf16 = N;
+      if ((rc = run_gemm2(A, B, gp, 1, bw->num_sms, st))) return rc;
+      x = y; K = N;
     }
-    rc = run_gemm(x, pl.BcPad, bw->headw, DAN_HEAD_PAD, nb, DAN_HEAD_PAD, KC, PART, DAN_HEAD_PAD, bw->num_sms, st);
-    if (rc) return rc;
-    { DanProfScope ps(DAN_PROF_POOL, st); heads_finish_kernel<<<grid_for((long)nb * DAN_NUM_HEAD_OUTPUTS), 256, 0, st>>>(PART, nb, m->headB, heads_out + (long)c0 * DAN_NUM_HEAD_OUTPUTS); }
-    dan_count_launch();
-    DAN_CUDA_TRY(cudaGetLastError());
+    {
+      Gemm2Operand A{x, nb, (long)K * 2, 0};
+      Gemm2Operand B{bw->headw, DAN_HEAD_PAD, (long)K * 2, 0};
+      Gemm2Params gp{};
+      gp.M = nb; gp.N = DAN_HEAD_PAD; gp.K = K; gp.mode = kG2Heads; gp.bias = m->headB;
+      gp.out = heads_out + (long)c0 * DAN_NUM_HEAD_OUTPUTS;
+      if ((rc = run_gemm2(A, B, gp, 1, bw->num_sms, st))) return rc;
+    }
   }
   return DAN_OK;
 }
@@ -1107,8 +951,7 @@ __global__ void fcin_to_reference_order_kernel(const uint4* __restrict__ fcin, l
       const int o = rem / R, r = rem % R;
       k = pooled + ((long)l * R + r) * bott + o;
     }
-    const __nv_bfloat16* piece = reinterpret_cast<const __nv_bfloat16*>(fcin + (k / 8) * kstride + m);
-    out[i] = __bfloat162float(piece[k % 8]);
+    out[i] = __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(fcin + m * kstride)[k]);      // kstride = pieces per row
   }
 }
 }  // namespace
@@ -1117,7 +960,7 @@ int dan_bf16_debug_fc_input(dan_model* m, int batch, const void* ws, float* out,
   const Bf16Plan pl = make_plan(m, batch);
   const int nb = batch % pl.Bc == 0 ? pl.Bc : batch % pl.Bc;
   const uint4* FCIN = reinterpret_cast<const uint4*>(static_cast<const char*>(ws) + pl.off_fcin);
-  fcin_to_reference_order_kernel<<<grid_for((long)nb * m->fcIn), 256, 0, st>>>(FCIN, pl.BcPad, nb, out, m->fcIn, m->pooled, m->P, kC, m->R, m->bott > 0 ? m->bott : 1);
+  fcin_to_reference_order_kernel<<<grid_for((long)nb * m->fcIn), 256, 0, st>>>(FCIN, pl.fcKC, nb, out, m->fcIn, m->pooled, m->P, kC, m->R, m->bott > 0 ? m->bott : 1);
   DAN_CUDA_TRY(cudaGetLastError());
   return nb;
 }

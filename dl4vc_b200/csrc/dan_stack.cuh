@@ -45,7 +45,7 @@ struct StackLayer {
   size_t wreplica_stride;   // byte distance between the kWeightReplicas copies of wstream
   const float* chan;        // [4][128]: conv bias, BN scale, BN shift, residual bias
   const float* bbias;       // [bott]
-  uint4* tout;              // T[p][c8][read][8] of this layer
+  uint4* tout;              // T[read][p][bott] (bf16) of this layer: row-major A operand of the compression GEMM
   int conv_blocks;          // 3 * kc_in / 2
   int kc_in;                // 16-byte pieces per input row (CinPad/8 for layer 1, else 16)
   int dil, residual, highway;
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
                 o.y = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 2]) + bb[g * 8 + 2], 0.f), fmaxf(__uint_as_float(r[g * 8 + 3]) + bb[g * 8 + 3], 0.f));
                 o.z = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 4]) + bb[g * 8 + 4], 0.f), fmaxf(__uint_as_float(r[g * 8 + 5]) + bb[g * 8 + 5], 0.f));
                 o.w = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 6]) + bb[g * 8 + 6], 0.f), fmaxf(__uint_as_float(r[g * 8 + 7]) + bb[g * 8 + 7], 0.f));
-                L.tout[((long)pos * c8n + cc * 4 + g) * p.t_reads_stride + (r_begin + i)] = o;
+                L.tout[((long)(r_begin + i) * p.P + pos) * c8n + cc * 4 + g] = o;
               }
             }
           }
