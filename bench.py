@@ -290,7 +290,7 @@ def run_b200(args):
     achieved = flops_per_launch / (dom_ms_step / dom_launches * 1e-3) / 1e12 if dom_ms_step > 0 else 0.0
     peak = peaks["bf16_sustained"] if args.precision == "bf16" else None
     roofline = {
-        "bound": "tensor", "kernel": "dan_layer_kernel (conv stack class)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+        "bound": "tensor", "kernel": "dan_stack_kernel (conv stack class)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if peak else None, "traffic": None,
         "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); burst {peaks['bf16_burst']}",
         "launches_per_step": dom_launches, "avg_launch_ms": dom_ms_step / dom_launches,

@@ -848,8 +848,8 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
             cudaFree(sp.prof);
             double a[16] = {0};
             for (int c = 0; c < grid; ++c) for (int k = 0; k < 16; ++k) a[k] += (double)h[c * 16 + k] / grid;
-            fprintf(stderr, "[stackprof] layers %d-%d reads %d grid %d: issuer0 total %.0f dep-wait %.0f | epi0 wait %.0f main %.0f bott %.0f | epi1 wait %.0f main %.0f bott %.0f | store+load wait %.0f %.0f | issuer1 total %.0f dep-wait %.0f (cycles, mean over CTAs)\n",
-                    l + 1, l_end, sp.num_reads, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11]);
+            fprintf(stderr, "[stackprof] layers %d-%d reads %d grid %d: issuer0 total %.0f dep-wait %.0f | epi0 wait %.0f main %.0f bott %.0f | epi1 wait %.0f main %.0f bott %.0f | store+load wait %.0f %.0f | issuer1 total %.0f dep-wait %.0f | weight-wait %.0f %.0f (cycles, mean over CTAs)\n",
+                    l + 1, l_end, sp.num_reads, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13]);
           }
           if (m->cfg.pool_after[l_end - 1] && l_end < L) {
             { DanProfScope ps(DAN_PROF_POOL, st); pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(next, pl.kstride, POOL, g); }

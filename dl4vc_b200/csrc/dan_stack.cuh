@@ -241,7 +241,13 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     constexpr uint32_t kStep = 2 * (kStkPlane >> 4);                                              // one k-step = two chunk planes
     uint32_t wi = 0, wp = 0, opc = 0;
     const long long t_begin = clock64();
-    long long t_dep = 0;
+    long long t_dep = 0, t_wfull = 0;
+    const bool do_mma = !(p.debug & 1);
+    auto wait_w = [&]() {
+      if (p.prof) { const long long c0 = clock64(); mbar_wait(&wfull[wi], wp); t_wfull += clock64() - c0; }
+      else mbar_wait(&wfull[wi], wp);
+      tc_fence_after();
+    };
     auto wait_dep = [&](bool first_of_read, int k) {
       long long c0 = 0; if (p.prof) c0 = clock64();
       mbar_wait(&sm->act_ready[s], opc & 1);
@@ -271,10 +277,9 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           for (int tap = 0; tap < 3; ++tap) {
             uint32_t bd_lo = (x_lo - dil + (uint32_t)tap * dil) | b_lbo_x;
             for (int j = 0; j < ksteps; j += 2) {
-              mbar_wait(&wfull[wi], wp);
-              tc_fence_after();
+              wait_w();
               const uint32_t a_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w;
-              if (elect_one()) {
+              if (do_mma && elect_one()) {
                 umma_bf16(d_main, stk_desc(a_lo, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, acc);
                 umma_bf16(d_main, stk_desc(a_lo + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
               }
@@ -288,13 +293,12 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           uint32_t bd_lo = x_lo - dil;
           int jj = 0;
           for (int blk = 0; blk < total; blk += 2) {
-            mbar_wait(&wfull[wi], wp);
-            tc_fence_after();
+            wait_w();
             const uint32_t a_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w;
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               if (blk + u < total) {
-                if (elect_one()) umma_bf16(d_main, stk_desc(a_lo + u * 256u, desc_hi), stk_desc(bd_lo | b_lbo_x, desc_hi), idesc_main, (blk + u) > 0);
+                if (do_mma && elect_one()) umma_bf16(d_main, stk_desc(a_lo + u * 256u, desc_hi), stk_desc(bd_lo | b_lbo_x, desc_hi), idesc_main, (blk + u) > 0);
                 __syncwarp();
                 bd_lo += kStep;
                 if (++jj == ksteps) { jj = 0; bd_lo += dil - (uint32_t)ksteps * kStep; }
@@ -309,10 +313,9 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           wait_dep(false, 0);
           uint32_t bd_lo = x_lo | b_lbo_x;
           for (int blk = 0; blk < kKC / 2; blk += 2) {
-            mbar_wait(&wfull[wi], wp);
-            tc_fence_after();
+            wait_w();
             const uint32_t a_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w;
-            if (elect_one()) {
+            if (do_mma && elect_one()) {
               umma_bf16(d_main, stk_desc(a_lo, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, 1);
               umma_bf16(d_main, stk_desc(a_lo + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
             }
@@ -327,11 +330,10 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           wait_dep(false, 0);
           uint32_t xa_lo = x_lo | b_lbo_x;
           for (int blk = 0; blk < kKC / 2; blk += bott_per_stage) {
-            mbar_wait(&wfull[wi], wp);
-            tc_fence_after();
+            wait_w();
             uint32_t w_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | b_lbo_bott;
             for (int u = 0; u < bott_per_stage; ++u) {
-              if (elect_one()) {
+              if (do_mma && elect_one()) {
                 umma_bf16(d_main, stk_desc(xa_lo, desc_hi), stk_desc(w_lo, desc_hi), idesc_bott, (blk + u) > 0);
                 umma_bf16(d_main + (uint32_t)p.bott, stk_desc(xa_lo + 128u, desc_hi), stk_desc(w_lo, desc_hi), idesc_bott, (blk + u) > 0);
               }
@@ -345,7 +347,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         }
       }
     }
-    if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 0 + 10 * s] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 1 + 10 * s] = t_dep; }
+    if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 0 + 10 * s] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 1 + 10 * s] = t_dep; p.prof[blockIdx.x * 16 + 12 + s] = t_wfull; }
   } else {
     // ===================== epilogue warps of slot s: quadrant q = TMEM lanes / channels 32q.., half h = position range;
     // thread 0 of the slot's group also moves the slot's reads in and out ==========================================
@@ -376,7 +378,9 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         mbar_wait(&sm->acc_full[s], opc & 1);
         tc_fence_after();
         if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-        if (L.residual) stack_epi_main<kEpiPreRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
+        const bool do_epi = !(p.debug & 2);
+        if (!do_epi) {}
+        else if (L.residual) stack_epi_main<kEpiPreRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
         else stack_epi_main<kEpiFinal>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
         fence_proxy_async_smem();
         tc_fence_before();
@@ -387,7 +391,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           mbar_wait(&sm->acc_full[s], opc & 1);
           tc_fence_after();
           if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-          stack_epi_main<kEpiPostRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
+          if (do_epi) stack_epi_main<kEpiPostRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(&sm->act_ready[s]);
@@ -402,7 +406,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           // bottleneck tile h: TMEM lane = position 128h + 32q + lane, columns = bottleneck channels
           const int c8n = p.bott / 8;
           const int pos = 128 * h + 32 * q + lane;
-          for (int cc = 0; cc < p.bott / 32; ++cc) {
+          for (int cc = 0; do_epi && cc < p.bott / 32; ++cc) {
             uint32_t r[32];
             tmem_ld32(tbase + (uint32_t)(h * p.bott + cc * 32), r);
             tmem_ld_wait();
