@@ -15,7 +15,7 @@ NUM_HEAD_OUTPUTS = 27
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdan_b200.so")
+LIB_PATH = os.environ.get("DAN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdan_b200.so")   # override: A/B builds during development
 
 # every symbol include/dan_b200.h declares (checked by tests/test_capi_symbols.py)
 EXPORTED_SYMBOLS = (

@@ -375,7 +375,7 @@ __global__ void __launch_bounds__(kLayerThreads, 1) dan_layer_kernel(const __gri
               for (int j = 0; j < 8; ++j) f[j] = fmaxf(__uint_as_float(r[g * 8 + j]) + p.bbias[c * 32 + g * 8 + j], 0.f);   // model.py:774
               uint4 o;
               o.x = pack_bf16x2(f[0], f[1]); o.y = pack_bf16x2(f[2], f[3]); o.z = pack_bf16x2(f[4], f[5]); o.w = pack_bf16x2(f[6], f[7]);
-              p.tout[((long)read * p.P + pp) * (p.bott / 8) + c * 4 + g] = o;
+              p.tout[((long)read * (p.bott / 8) + c * 4 + g) * p.P + pp] = o;
             }
           }
         }
@@ -520,7 +520,7 @@ __global__ void pack_conv_bf16_kernel(const float* __restrict__ w, uint4* __rest
 // linear-like (N, K) fp32 with optional source-column map -> bf16 row-major [Npad][Kpad] (mode 3: UMMA chunk image [kc][Npad][8])
 __global__ void pack_linear_bf16_kernel(const float* __restrict__ w, uint4* __restrict__ out, int N, int Npad, int K, int Kpad,
                                         int mode, int P, int C, int R, int bott, int L, int pooled, int skip_max) {
-  // mode 0: identity columns. mode 1: FC1 feature permutation (see dan_bf16_forward). mode 2: compression (O, Cb, 1, P): k = p*bott + c
+  // mode 0: identity columns. mode 1: FC1 feature permutation (see dan_bf16_forward). mode 2: compression (O, Cb, 1, P): k = ((c/8)*P + p)*8 + c%8
   const long total = (long)(Kpad / 8) * Npad * 8;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int j = (int)(i & 7); long t = i >> 3;
@@ -541,8 +541,9 @@ __global__ void pack_linear_bf16_kernel(const float* __restrict__ w, uint4* __re
           const int r = (int)(lr % R); const int l = (int)(lr / R);
           src = pooled + (long)l * bott * R + (long)o * R + r;
         }
-      } else if (mode == 2) {
-        const int c = (int)(k % bott), pp = (int)(k / bott);
+      } else if (mode == 2) {                             // K order of the T matrix: (c / 8, p, c % 8)
+        const int g = (int)(k / (P * 8)), rem = (int)(k % (P * 8));
+        const int pp = rem / 8, c = g * 8 + rem % 8;
         src = (long)c * P + pp;                           // within row n: (c, p)
       }
       v = w[(long)n * K + src];
@@ -766,7 +767,9 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
     if (m->cfg.is_residual[l] && m->cfg.pool_after[l - 1]) fused = false;
   static thread_local bool stack_attr_set = false;
   if (fused && !stack_attr_set) {
-    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
+    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
+    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
+    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
     stack_attr_set = true;
   }
   // layer-wise path: halo rows (and the rows past the last tile) must read as zero: clear the row matrices once per call.
@@ -828,9 +831,12 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           static const bool stack_prof = getenv("DAN_B200_STACKPROF") != nullptr;     // development aid: per-role cycle counters
           static const bool stack_trace = getenv("DAN_B200_STACKTRACE") != nullptr;
           static int trace_dumps = 0;
-          if (stack_trace && trace_dumps < 2 && sp.num_layers > 2) { sp.trace_cap = 6000; DAN_CUDA_TRY(cudaMalloc(&sp.trace, sizeof(uint2) * sp.trace_cap)); DAN_CUDA_TRY(cudaMemsetAsync(sp.trace, 0, sizeof(uint2) * sp.trace_cap, st)); }
+          if (stack_trace && trace_dumps < 2 && sp.num_layers > 2) { sp.trace_cap = 8000; DAN_CUDA_TRY(cudaMalloc(&sp.trace, sizeof(uint2) * sp.trace_cap)); DAN_CUDA_TRY(cudaMemsetAsync(sp.trace, 0, sizeof(uint2) * sp.trace_cap, st)); }
           if (stack_prof) { DAN_CUDA_TRY(cudaMalloc(&sp.prof, sizeof(unsigned long long) * 16 * grid)); DAN_CUDA_TRY(cudaMemsetAsync(sp.prof, 0, sizeof(unsigned long long) * 16 * grid, st)); }
-          { DanProfScope ps(DAN_PROF_CONV_STACK, st); dan_stack_kernel<<<grid, kStkThreads, kStkSmemBytes, st>>>(sp); }
+          { DanProfScope ps(DAN_PROF_CONV_STACK, st);
+            if (sp.prof || sp.trace) dan_stack_kernel<2><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);        // development builds of the kernel
+            else if (sp.debug) dan_stack_kernel<1><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);
+            else dan_stack_kernel<0><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp); }
           dan_count_launch();
           DAN_CUDA_TRY(cudaGetLastError());
           if (sp.trace) {
@@ -839,7 +845,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
             DAN_CUDA_TRY(cudaMemcpy(h.data(), sp.trace, h.size() * sizeof(uint2), cudaMemcpyDeviceToHost));
             cudaFree(sp.trace);
             char name[64]; snprintf(name, sizeof(name), "gpurun_out/stack_trace_%d.txt", trace_dumps++);
-            if (FILE* f = fopen(name, "w")) { const int n = (int)h[0].x < sp.trace_cap - 1 ? (int)h[0].x : sp.trace_cap - 1; for (int k = 1; k <= n; ++k) fprintf(f, "%x %u\n", h[k].x, h[k].y); fclose(f); }
+            if (FILE* f = fopen(name, "w")) { for (int k = 0; k < sp.trace_cap; ++k) if (h[k].y) fprintf(f, "%x %u\n", h[k].x, h[k].y); fclose(f); }
           }
           if (stack_prof) {
             std::vector<unsigned long long> h(16 * (size_t)grid);

@@ -35,17 +35,18 @@ constexpr int kStkRB = kStkLead + kStkN + 2;   // rows per channel-chunk plane o
 constexpr int kStkPlane = kStkRB * 16;         // bytes per plane (3392)
 constexpr int kStkBuf = kKC * kStkPlane;       // bytes per read buffer (54272)
 constexpr int kStkStageBytes = 8192;   // weight-ring stage = two k-step blocks of 4 KB
-constexpr int kStkStages = 7;          // stages per slot
+constexpr int kStkStages = 14;         // stages of the weight ring shared by the two slots (>= largest op (12) + prefetch)
 constexpr int kStkMaxSeg = 8;          // layers per segment
+constexpr int kStkRegsIssue = 56, kStkRegsEpi = 104;   // setmaxnreg redistributes the launch allocation (640 x 96): 128 x 56 + 512 x 104 = 60416 <= 61440
 constexpr int kStkSmemHeader = 3072;   // barriers, TMEM pointer, bottleneck biases of the segment
-constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + 2 * kStkStages * kStkStageBytes;
+constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + kStkStages * kStkStageBytes;
 
 struct StackLayer {
   const uint8_t* wstream;   // conv k-step blocks (tap-major) | residual blocks | bottleneck blocks, contiguous
   size_t wreplica_stride;   // byte distance between the kWeightReplicas copies of wstream
   const float* chan;        // [4][128]: conv bias, BN scale, BN shift, residual bias
   const float* bbias;       // [bott]
-  uint4* tout;              // T[read][p][bott] (bf16) of this layer: row-major A operand of the compression GEMM
+  uint4* tout;              // T[read][c/8][p][c%8] (bf16) of this layer: row-major A operand (K = (c/8, p, c%8)) of the compression GEMM
   int conv_blocks;          // 3 * kc_in / 2
   int kc_in;                // 16-byte pieces per input row (CinPad/8 for layer 1, else 16)
   int dil, residual, highway;
@@ -63,94 +64,33 @@ struct StackParams {
 };
 
 struct StackSmem {
-  uint64_t w_full[2][kStkStages], w_empty[2][kStkStages];
+  uint64_t w_full[kStkStages], w_empty[kStkStages];
   uint64_t acc_full[2], act_ready[2], in_full[2];
   uint32_t tmem_base;
+  uint32_t issued_ops;                 // ops fully issued by slot 0's issuer (slot 1 runs one op behind, see the issuer)
   float bbias[kStkMaxSeg][64];
 };
 static_assert(sizeof(StackSmem) <= kStkSmemHeader, "header too small");
 
-enum { kEpiFinal = 0, kEpiPreRes = 1, kEpiPostRes = 2 };
-
-// ---- main-accumulator epilogue (see header comment). A warp owns TMEM lane quadrant q (channels 32q..32q+31) and a
-// range of 8-position groups; it walks the range in chunks of two groups (16 positions) with the TMEM load of the
-// next chunk in flight while the current one is converted and written. ----
-// y = s*relu(z + b) + t (ReLU then BatchNorm, model.py:749-751) is evaluated as one FFMA and one predicated min/max:
-//   s >= 0: max(s*z + c, t),  s < 0: min(s*z + c, t),  c = s*b + t
-struct EpiConsts { float scale[4], c[4], shift[4], rbias[4]; bool pos[4]; };
-
-__device__ __forceinline__ void stack_epi_load(uint32_t tbase, int g0, uint32_t (&r0)[8], uint32_t (&r1)[8]) {
-  tmem_ld_16x256b_x2(tbase + g0 * 8, r0);
-  tmem_ld_16x256b_x2(tbase + (16u << 16) + g0 * 8, r1);
-}
-
-template <int MODE, bool MASK>
-__device__ __forceinline__ void stack_epi_chunk(const uint32_t (&r0)[8], const uint32_t (&r1)[8], uint32_t tbase, uint32_t saddr0, int g0, int lane,
-                                                int P, const EpiConsts& k) {
-  uint32_t x0[8], x1[8];
-#pragma unroll
-  for (int gi = 0; gi < 2; ++gi) {
-    // this thread's row of the four 8x8 blocks (channel chunks 4q..4q+3) of position group g0+gi
-    const uint32_t saddr = saddr0 + (uint32_t)(g0 + gi) * 128u;
-    uint32_t pk[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const uint32_t* src = (j < 2) ? r0 : r1;
-      float lo = __uint_as_float(src[4 * gi + 2 * (j & 1)]), hi = __uint_as_float(src[4 * gi + 2 * (j & 1) + 1]);
-      if constexpr (MODE != kEpiPostRes) {
-        lo = fmaf(lo, k.scale[j], k.c[j]); hi = fmaf(hi, k.scale[j], k.c[j]);
-        lo = k.pos[j] ? fmaxf(lo, k.shift[j]) : fminf(lo, k.shift[j]);
-        hi = k.pos[j] ? fmaxf(hi, k.shift[j]) : fminf(hi, k.shift[j]);
-      }
-      if constexpr (MASK) {                                                   // positions >= P are the zero rows behind the read
-        const int pos = 8 * (g0 + gi) + 2 * (lane & 3);
-        lo = pos < P ? lo : 0.f; hi = pos + 1 < P ? hi : 0.f;
-      }
-      pk[j] = pack_bf16x2(lo, hi);
-    }
-    if constexpr (MODE == kEpiPreRes) {
-      uint32_t xin[4];
-      ldmatrix_x4_trans(saddr, xin[0], xin[1], xin[2], xin[3]);        // layer input x (model.py:732), same fragment layout
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        uint32_t* dst = (j < 2) ? x0 : x1;
-        dst[4 * gi + 2 * (j & 1)] = __float_as_uint(bf16_lo(xin[j]) + k.rbias[j]);
-        dst[4 * gi + 2 * (j & 1) + 1] = __float_as_uint(bf16_hi(xin[j]) + k.rbias[j]);
-      }
-    }
-    stmatrix_x4_trans(saddr, pk[0], pk[1], pk[2], pk[3]);
-  }
-  if constexpr (MODE == kEpiPreRes) {     // accumulator := x + b_res; the residual 1x1 MMA accumulates on top (model.py:760-761)
-    tmem_st_16x256b_x2(tbase + g0 * 8, x0);
-    tmem_st_16x256b_x2(tbase + (16u << 16) + g0 * 8, x1);
-  }
-}
-
-// groups [g_begin, g_end), (g_end - g_begin) a multiple of 2; the chunk containing group 25 masks positions >= P
-template <int MODE>
-__device__ __forceinline__ void stack_epi_main(uint32_t tbase, uint32_t saddr0, int lane, int P, int g_begin, int g_end, const EpiConsts& k) {
-#pragma unroll 1
-  for (int g0 = g_begin; g0 < g_end; g0 += 2) {
-    uint32_t a0[8], a1[8];
-    stack_epi_load(tbase, g0, a0, a1);
-    tmem_ld_wait();
-    if (g0 == 24) stack_epi_chunk<MODE, true>(a0, a1, tbase, saddr0, g0, lane, P, k);
-    else stack_epi_chunk<MODE, false>(a0, a1, tbase, saddr0, g0, lane, P, k);
-  }
-  if constexpr (MODE == kEpiPreRes) tmem_st_wait();
-}
+}  // namespace
+#include "dan_stack_epi.cuh"
+namespace {
 
 // descriptor words: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14  (tcgen05_ptx.cuh make_smem_desc)
 __device__ __forceinline__ uint64_t stk_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-__device__ __forceinline__ void stk_trace(const StackParams& p, uint32_t id) {
+// role = 0,1 issuer of slot 0,1; 2,3 epilogue of slot 0,1: each role logs into its own quarter of the buffer (no atomics)
+__device__ __forceinline__ void stk_trace(const StackParams& p, int role, int& n, uint32_t id) {
   if (p.trace && blockIdx.x == 0) {
-    const uint32_t k = atomicAdd(&p.trace[0].x, 1u) + 1;
-    if ((int)k < p.trace_cap) p.trace[k] = make_uint2(id, (uint32_t)clock64());
+    const int cap = p.trace_cap / 4;
+    if (n < cap) p.trace[role * cap + n++] = make_uint2(id, (uint32_t)clock64());
   }
 }
 
+// kDev: 0 = production, 1 = honours the debug skip flags only, 2 = + cycle counters and event trace (development builds)
+template <int kDev>
 __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_constant__ StackParams p) {
+  const bool prof_on = kDev == 2 && p.prof != nullptr, trace_on = kDev == 2 && p.trace != nullptr;
   extern __shared__ __align__(1024) uint8_t smem[];
   StackSmem* sm = reinterpret_cast<StackSmem*>(smem);
   uint8_t* bufs = smem + kStkSmemHeader;
@@ -168,8 +108,9 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     for (int i = threadIdx.x; i < 2 * kStkBuf / 16; i += kStkThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
+    for (int i = 0; i < kStkStages; ++i) { mbar_init(&sm->w_full[i], 1); mbar_init(&sm->w_empty[i], 2); }   // both slots release a stage
+    sm->issued_ops = 0;
     for (int s = 0; s < 2; ++s) {
-      for (int i = 0; i < kStkStages; ++i) { mbar_init(&sm->w_full[s][i], 1); mbar_init(&sm->w_empty[s][i], 1); }
       mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], kStkEpiThreads); mbar_init(&sm->in_full[s], 1);
     }
     fence_mbar_init();
@@ -194,22 +135,27 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     for (int kc = 0; kc < in_kc; ++kc) bulk_g2s(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s]);
   };
 
+  // register budget: the producer / issuer warpgroup (warps 16-19) hands registers to the four epilogue warpgroups
+  if (warp >= 16) {
+#ifndef DAN_STK_NO_SETMAXNREG
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kStkRegsIssue));
+#endif
   if (warp == 16 || warp == 17) {
-    // ===================== weight producer of slot s: streams every op's A/B blocks in issue order =================
-    if (lane == 0) {
-      const int s = warp - 16;
-      uint8_t* ring = rings + (size_t)s * kStkStages * kStkStageBytes;
+    // ===================== weight producer: ONE stream for both slots. The two reads of a pair go through the same op
+    // sequence one op apart (see the issuers), so every stage is consumed twice before it is refilled: the L2 -> SMEM
+    // weight traffic (the binding resource of this kernel when each slot streamed its own copy) is halved. =========
+    if (warp == 16 && lane == 0) {
       uint32_t idx = 0, par = 1;     // first pass over the ring: the "empty" phase counts as complete
       auto emit = [&](const uint8_t* src, uint32_t bytes) {
         for (uint32_t off = 0; off < bytes; off += kStkStageBytes) {
           const uint32_t n = min((uint32_t)kStkStageBytes, bytes - off);
-          mbar_wait(&sm->w_empty[s][idx], par);
-          mbar_expect_tx(&sm->w_full[s][idx], n);
-          bulk_g2s(ring + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[s][idx]);
+          mbar_wait(&sm->w_empty[idx], par);
+          mbar_expect_tx(&sm->w_full[idx], n);
+          bulk_g2s(rings + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[idx]);
           if (++idx == kStkStages) { idx = 0; par ^= 1; }
         }
       };
-      for (int i = s; i < n_reads; i += 2) {
+      for (int i = 0; i < n_reads; i += 2) {
         for (int l = 0; l < p.num_layers; ++l) {
           const StackLayer& L = p.layer[l];
           const uint32_t conv_bytes = (uint32_t)L.conv_blocks * 4096u;
@@ -220,7 +166,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         }
       }
     }
-  } else if (warp == 18 || warp == 19) {
+  } else {
     // ===================== MMA issuer of slot s. The whole warp runs the (blocking, strictly sequential) op schedule of
     // its slot — warp-uniform control flow keeps descriptors in uniform registers — and one elected lane issues the
     // tcgen05 instructions. The two slots' issuers are independent warps: the tensor pipe interleaves their MMA
@@ -233,31 +179,44 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
     const uint32_t a_lbo_w = (2048u >> 4) << 16, b_lbo_x = ((uint32_t)kStkPlane >> 4) << 16, b_lbo_bott = (((uint32_t)p.bott * 16u) >> 4) << 16;
     const int bott_per_stage = kStkStageBytes / (p.bott * 32);
-    const uint32_t ring_lo = (smem_u32(rings) >> 4) + (uint32_t)s * kStkStages * (kStkStageBytes >> 4);
-    uint64_t* const wfull = &sm->w_full[s][0];
-    uint64_t* const wempty = &sm->w_empty[s][0];
+    const uint32_t ring_lo = smem_u32(rings) >> 4;
+    uint64_t* const wfull = &sm->w_full[0];
+    uint64_t* const wempty = &sm->w_empty[0];
+    volatile uint32_t* const issued = &sm->issued_ops;
+    uint32_t gops = 0;                                                                            // ops started by this issuer
+    int tr_n = 0;
     const uint32_t d_main = tmem_base + (uint32_t)s * 256u;
     const uint32_t x_lo = (smem_u32(bufs) >> 4) + (uint32_t)s * (kStkBuf >> 4) + kStkLead;       // centre row of chunk plane 0
     constexpr uint32_t kStep = 2 * (kStkPlane >> 4);                                              // one k-step = two chunk planes
     uint32_t wi = 0, wp = 0, opc = 0;
     const long long t_begin = clock64();
     long long t_dep = 0, t_wfull = 0;
-    const bool do_mma = !(p.debug & 1);
+    const bool do_mma = kDev == 0 || !(p.debug & 1);
     auto wait_w = [&]() {
-      if (p.prof) { const long long c0 = clock64(); mbar_wait(&wfull[wi], wp); t_wfull += clock64() - c0; }
+      if (prof_on) { const long long c0 = clock64(); mbar_wait(&wfull[wi], wp); t_wfull += clock64() - c0; }
       else mbar_wait(&wfull[wi], wp);
       tc_fence_after();
     };
     auto wait_dep = [&](bool first_of_read, int k) {
-      long long c0 = 0; if (p.prof) c0 = clock64();
+      long long c0 = 0; if (prof_on) c0 = clock64();
+      // slot 1 starts op n only after slot 0 has issued all of its op n: the tensor pipe then runs slot 1's MMAs under slot 0's
+      // epilogue (and vice versa) instead of both slots computing and then both draining, and the lag between the two
+      // consumers of the shared weight ring stays within one op (<= 12 of the 14 stages).
+      if (s == 1) { uint32_t spins = 0; while (*issued <= gops) { if (++spins > (1u << 28)) __trap(); } }
+      ++gops;
       mbar_wait(&sm->act_ready[s], opc & 1);
       if (first_of_read) mbar_wait(&sm->in_full[s], (uint32_t)k & 1);
       tc_fence_after();
-      if (p.prof) t_dep += clock64() - c0;
+      if (prof_on) t_dep += clock64() - c0;
+      if (trace_on && lane == 0) stk_trace(p, s, tr_n, (uint32_t)s << 28 | 1u << 24 | (gops & 0xFFFFu));
     };
     auto op_done = [&]() {
-      if (elect_one()) umma_commit(&sm->acc_full[s]);
+      if (elect_one()) {
+        umma_commit(&sm->acc_full[s]);
+        if (s == 0) { __threadfence_block(); *issued = gops; }
+      }
       __syncwarp();
+      if (trace_on && lane == 0) stk_trace(p, s, tr_n, (uint32_t)s << 28 | 2u << 24 | (gops & 0xFFFFu));
       ++opc;
     };
     auto stage_done = [&]() {
@@ -265,7 +224,21 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       __syncwarp();
       if (++wi == kStkStages) { wi = 0; wp ^= 1; }
     };
-    for (int i = s, k = 0; i < n_reads; i += 2, ++k) {
+    for (int i = s, k = 0; i < n_reads + (n_reads & 1); i += 2, ++k) {
+      if (i >= n_reads) {
+        // odd tail: slot 1 has no read in the last pair but must still release the stages streamed for slot 0's read
+        for (int l = 0; l < p.num_layers; ++l) {
+          const StackLayer& L = p.layer[l];
+          const int stages = (L.conv_blocks + 1) / 2 + (L.residual ? kKC / 4 : 0) + (L.highway ? p.bott / 32 : 0);
+          for (int st = 0; st < stages; ++st) {
+            mbar_wait(&wfull[wi], wp);
+            if (elect_one()) mbar_arrive(&wempty[wi]);
+            __syncwarp();
+            if (++wi == kStkStages) { wi = 0; wp ^= 1; }
+          }
+        }
+        break;
+      }
       for (int l = 0; l < p.num_layers; ++l) {
         const StackLayer& L = p.layer[l];
         const int residual = L.residual, highway = L.highway, ksteps = L.kc_in / 2, total = L.conv_blocks;
@@ -347,8 +320,12 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         }
       }
     }
-    if (p.prof && lane == 0) { p.prof[blockIdx.x * 16 + 0 + 10 * s] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 1 + 10 * s] = t_dep; p.prof[blockIdx.x * 16 + 12 + s] = t_wfull; }
+    if (prof_on && lane == 0) { p.prof[blockIdx.x * 16 + 0 + 10 * s] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 1 + 10 * s] = t_dep; p.prof[blockIdx.x * 16 + 12 + s] = t_wfull; }
+  }
   } else {
+#ifndef DAN_STK_NO_SETMAXNREG
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kStkRegsEpi));
+#endif
     // ===================== epilogue warps of slot s: quadrant q = TMEM lanes / channels 32q.., half h = position range;
     // thread 0 of the slot's group also moves the slot's reads in and out ==========================================
     const int s = warp >> 3, h = (warp >> 2) & 1, q = warp & 3;
@@ -360,9 +337,10 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     const int g_begin = h == 0 ? 0 : 14, g_end = h == 0 ? 14 : 26;
     if (gtid == 0 && s < n_reads) load_read(s);
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
-    uint32_t opc = 0;
+    uint32_t opc = 0, eops = 0;
+    int tr_n = 0;
     long long t_wait = 0, t_main = 0, t_bott = 0, t_io = 0, t0 = 0;
-    const bool prof = p.prof != nullptr && gtid == 0;
+    const bool prof = prof_on && gtid == 0;
     for (int i = s; i < n_reads; i += 2) {
       for (int l = 0; l < p.num_layers; ++l) {
         const StackLayer& L = p.layer[l];
@@ -371,14 +349,15 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         for (int j = 0; j < 4; ++j) {
           const int c = 32 * q + 8 * j + (lane >> 2);
           const float b = __ldg(L.chan + c);
-          k.scale[j] = __ldg(L.chan + kC + c); k.shift[j] = __ldg(L.chan + 2 * kC + c); k.rbias[j] = __ldg(L.chan + 3 * kC + c);
-          k.c[j] = fmaf(k.scale[j], b, k.shift[j]); k.pos[j] = k.scale[j] >= 0.f;
+          k.scale[j] = __ldg(L.chan + kC + c); k.rbias[j] = __ldg(L.chan + 3 * kC + c);
+          k.c[j] = fmaf(k.scale[j], b, __ldg(L.chan + 2 * kC + c)); k.nb[j] = -b;
         }
         if (prof) t0 = clock64();
         mbar_wait(&sm->acc_full[s], opc & 1);
         tc_fence_after();
         if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-        const bool do_epi = !(p.debug & 2);
+        if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 3u << 24 | (eops & 0xFFFFu));
+        const bool do_epi = kDev == 0 || !(p.debug & 2);
         if (!do_epi) {}
         else if (L.residual) stack_epi_main<kEpiPreRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
         else stack_epi_main<kEpiFinal>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
@@ -386,16 +365,19 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         tc_fence_before();
         mbar_arrive(&sm->act_ready[s]);
         ++opc;
+        if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
         if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
         if (L.residual) {
           mbar_wait(&sm->acc_full[s], opc & 1);
           tc_fence_after();
           if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 3u << 24 | (eops & 0xFFFFu));
           if (do_epi) stack_epi_main<kEpiPostRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
           fence_proxy_async_smem();
           tc_fence_before();
           mbar_arrive(&sm->act_ready[s]);
           ++opc;
+          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
           if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
         }
         const bool last = l + 1 == p.num_layers;
@@ -403,6 +385,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           mbar_wait(&sm->acc_full[s], opc & 1);
           tc_fence_after();
           if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
+          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 3u << 24 | (eops & 0xFFFFu));
           // bottleneck tile h: TMEM lane = position 128h + 32q + lane, columns = bottleneck channels
           const int c8n = p.bott / 8;
           const int pos = 128 * h + 32 * q + lane;
@@ -419,13 +402,14 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
                 o.y = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 2]) + bb[g * 8 + 2], 0.f), fmaxf(__uint_as_float(r[g * 8 + 3]) + bb[g * 8 + 3], 0.f));
                 o.z = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 4]) + bb[g * 8 + 4], 0.f), fmaxf(__uint_as_float(r[g * 8 + 5]) + bb[g * 8 + 5], 0.f));
                 o.w = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 6]) + bb[g * 8 + 6], 0.f), fmaxf(__uint_as_float(r[g * 8 + 7]) + bb[g * 8 + 7], 0.f));
-                L.tout[((long)(r_begin + i) * p.P + pos) * c8n + cc * 4 + g] = o;
+                if (kDev == 0 || !(p.debug & 4)) L.tout[((long)(r_begin + i) * c8n + cc * 4 + g) * p.P + pos] = o;     // lanes = consecutive positions: 512 contiguous bytes per warp store
               }
             }
           }
           tc_fence_before();
           if (!last) mbar_arrive(&sm->act_ready[s]);
           ++opc;
+          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
           if (prof) { const long long t1 = clock64(); t_bott += t1 - t0; t0 = t1; }
         }
         if (last) {
@@ -440,6 +424,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             if (i + 2 < n_reads) load_read(i + 2);
           }
           if (L.highway) mbar_arrive(&sm->act_ready[s]);
+          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 5u << 24 | (eops & 0xFFFFu));
           if (prof) { const long long t1 = clock64(); t_io += t1 - t0; t0 = t1; }
         }
       }
