@@ -770,6 +770,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
     DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
     DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
     DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
+    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
     stack_attr_set = true;
   }
   // layer-wise path: halo rows (and the rows past the last tile) must read as zero: clear the row matrices once per call.
@@ -834,7 +835,8 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           if (stack_trace && trace_dumps < 2 && sp.num_layers > 2) { sp.trace_cap = 8000; DAN_CUDA_TRY(cudaMalloc(&sp.trace, sizeof(uint2) * sp.trace_cap)); DAN_CUDA_TRY(cudaMemsetAsync(sp.trace, 0, sizeof(uint2) * sp.trace_cap, st)); }
           if (stack_prof) { DAN_CUDA_TRY(cudaMalloc(&sp.prof, sizeof(unsigned long long) * 16 * grid)); DAN_CUDA_TRY(cudaMemsetAsync(sp.prof, 0, sizeof(unsigned long long) * 16 * grid, st)); }
           { DanProfScope ps(DAN_PROF_CONV_STACK, st);
-            if (sp.prof || sp.trace) dan_stack_kernel<2><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);        // development builds of the kernel
+            if (sp.trace) dan_stack_kernel<3><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);                  // development builds of the kernel
+            else if (sp.prof) dan_stack_kernel<2><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);
             else if (sp.debug) dan_stack_kernel<1><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);
             else dan_stack_kernel<0><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp); }
           dan_count_launch();

@@ -87,10 +87,10 @@ __device__ __forceinline__ void stk_trace(const StackParams& p, int role, int& n
   }
 }
 
-// kDev: 0 = production, 1 = honours the debug skip flags only, 2 = + cycle counters and event trace (development builds)
+// kDev: 0 = production, 1 = honours the debug skip flags only, 2 = + cycle counters, 3 = + event trace instead (development builds)
 template <int kDev>
 __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_constant__ StackParams p) {
-  const bool prof_on = kDev == 2 && p.prof != nullptr, trace_on = kDev == 2 && p.trace != nullptr;
+  const bool prof_on = kDev == 2 && p.prof != nullptr, trace_on = kDev == 3 && p.trace != nullptr;
   extern __shared__ __align__(1024) uint8_t smem[];
   StackSmem* sm = reinterpret_cast<StackSmem*>(smem);
   uint8_t* bufs = smem + kStkSmemHeader;
@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     // ===================== weight producer: ONE stream for both slots. The two reads of a pair go through the same op
     // sequence one op apart (see the issuers), so every stage is consumed twice before it is refilled: the L2 -> SMEM
     // weight traffic (the binding resource of this kernel when each slot streamed its own copy) is halved. =========
-    if (warp == 16 && lane == 0) {
+    if (warp == 16 && lane == 0 && !(kDev != 0 && (p.debug & 16))) {
       uint32_t idx = 0, par = 1;     // first pass over the ring: the "empty" phase counts as complete
       auto emit = [&](const uint8_t* src, uint32_t bytes) {
         for (uint32_t off = 0; off < bytes; off += kStkStageBytes) {
@@ -192,17 +192,26 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     const long long t_begin = clock64();
     long long t_dep = 0, t_wfull = 0;
     const bool do_mma = kDev == 0 || !(p.debug & 1);
+    const bool no_w = kDev != 0 && (p.debug & 16);     // development: weights are not streamed (garbage operands, timing only)
     auto wait_w = [&]() {
+      if (no_w) return;
       if (prof_on) { const long long c0 = clock64(); mbar_wait(&wfull[wi], wp); t_wfull += clock64() - c0; }
       else mbar_wait(&wfull[wi], wp);
       tc_fence_after();
     };
+    auto wait_w2 = [&](uint32_t wi1, uint32_t wp1) {
+      if (no_w) return;
+      if (prof_on) { const long long c0 = clock64(); mbar_wait2(&wfull[wi], wp, &wfull[wi1], wp1); t_wfull += clock64() - c0; }
+      else mbar_wait2(&wfull[wi], wp, &wfull[wi1], wp1);
+      tc_fence_after();
+    };
+    auto adv2 = [&](uint32_t wi1, uint32_t wp1) { wi = wi1 + 1; wp = wp1; if (wi == kStkStages) { wi = 0; wp ^= 1; } };
     auto wait_dep = [&](bool first_of_read, int k) {
       long long c0 = 0; if (prof_on) c0 = clock64();
       // slot 1 starts op n only after slot 0 has issued all of its op n: the tensor pipe then runs slot 1's MMAs under slot 0's
       // epilogue (and vice versa) instead of both slots computing and then both draining, and the lag between the two
       // consumers of the shared weight ring stays within one op (<= 12 of the 14 stages).
-      if (s == 1) { uint32_t spins = 0; while (*issued <= gops) { if (++spins > (1u << 28)) __trap(); } }
+      if (s == 1 && !(p.debug & 8)) { uint32_t spins = 0; while (*issued <= gops) { if (++spins > (1u << 28)) __trap(); } }
       ++gops;
       mbar_wait(&sm->act_ready[s], opc & 1);
       if (first_of_read) mbar_wait(&sm->in_full[s], (uint32_t)k & 1);
@@ -220,7 +229,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       ++opc;
     };
     auto stage_done = [&]() {
-      if (elect_one()) umma_commit(&wempty[wi]);
+      if (!no_w && elect_one()) umma_commit(&wempty[wi]);
       __syncwarp();
       if (++wi == kStkStages) { wi = 0; wp ^= 1; }
     };
@@ -230,7 +239,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         for (int l = 0; l < p.num_layers; ++l) {
           const StackLayer& L = p.layer[l];
           const int stages = (L.conv_blocks + 1) / 2 + (L.residual ? kKC / 4 : 0) + (L.highway ? p.bott / 32 : 0);
-          for (int st = 0; st < stages; ++st) {
+          for (int st = 0; st < stages && !no_w; ++st) {
             mbar_wait(&wfull[wi], wp);
             if (elect_one()) mbar_arrive(&wempty[wi]);
             __syncwarp();
@@ -245,21 +254,30 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         const uint32_t dil = (uint32_t)L.dil;
         // ---- conv: D[cout][pos] = sum over taps and input-channel k-steps ----
         wait_dep(l == 0, k);
-        if ((ksteps & 1) == 0) {
+        if ((ksteps & 3) == 0) {
+          // two ring stages (4 k-steps) per iteration: both full-barrier probes are in flight together and the four MMAs and
+          // the two stage releases go out from one elected region — a single warp retires a dependent instruction only every
+          // few cycles, so per-stage bookkeeping (not the tensor pipe) bounds the issue rate when it is done stage by stage
           uint32_t acc = 0;
           for (int tap = 0; tap < 3; ++tap) {
             uint32_t bd_lo = (x_lo - dil + (uint32_t)tap * dil) | b_lbo_x;
-            for (int j = 0; j < ksteps; j += 2) {
-              wait_w();
-              const uint32_t a_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w;
-              if (do_mma && elect_one()) {
-                umma_bf16(d_main, stk_desc(a_lo, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, acc);
-                umma_bf16(d_main, stk_desc(a_lo + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
+            for (int j = 0; j < ksteps; j += 4) {
+              const uint32_t wi1 = wi + 1 == kStkStages ? 0u : wi + 1, wp1 = wi1 == 0 ? wp ^ 1u : wp;
+              wait_w2(wi1, wp1);
+              const uint32_t a0 = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w, a1 = (ring_lo + wi1 * (kStkStageBytes >> 4)) | a_lbo_w;
+              if (elect_one()) {
+                if (do_mma) {
+                  umma_bf16(d_main, stk_desc(a0, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, acc);
+                  umma_bf16(d_main, stk_desc(a0 + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
+                  umma_bf16(d_main, stk_desc(a1, desc_hi), stk_desc(bd_lo + 2 * kStep, desc_hi), idesc_main, 1);
+                  umma_bf16(d_main, stk_desc(a1 + 256u, desc_hi), stk_desc(bd_lo + 3 * kStep, desc_hi), idesc_main, 1);
+                }
+                if (!no_w) { umma_commit(&wempty[wi]); umma_commit(&wempty[wi1]); }
               }
               __syncwarp();
               acc = 1;
-              bd_lo += 2 * kStep;
-              stage_done();
+              bd_lo += 4 * kStep;
+              adv2(wi1, wp1);
             }
           }
         } else {
@@ -285,16 +303,22 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         if (residual) {
           wait_dep(false, 0);
           uint32_t bd_lo = x_lo | b_lbo_x;
-          for (int blk = 0; blk < kKC / 2; blk += 2) {
-            wait_w();
-            const uint32_t a_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w;
-            if (do_mma && elect_one()) {
-              umma_bf16(d_main, stk_desc(a_lo, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, 1);
-              umma_bf16(d_main, stk_desc(a_lo + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
+          for (int blk = 0; blk < kKC / 2; blk += 4) {
+            const uint32_t wi1 = wi + 1 == kStkStages ? 0u : wi + 1, wp1 = wi1 == 0 ? wp ^ 1u : wp;
+            wait_w2(wi1, wp1);
+            const uint32_t a0 = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w, a1 = (ring_lo + wi1 * (kStkStageBytes >> 4)) | a_lbo_w;
+            if (elect_one()) {
+              if (do_mma) {
+                umma_bf16(d_main, stk_desc(a0, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, 1);
+                umma_bf16(d_main, stk_desc(a0 + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
+                umma_bf16(d_main, stk_desc(a1, desc_hi), stk_desc(bd_lo + 2 * kStep, desc_hi), idesc_main, 1);
+                umma_bf16(d_main, stk_desc(a1 + 256u, desc_hi), stk_desc(bd_lo + 3 * kStep, desc_hi), idesc_main, 1);
+              }
+              if (!no_w) { umma_commit(&wempty[wi]); umma_commit(&wempty[wi1]); }
             }
             __syncwarp();
-            bd_lo += 2 * kStep;
-            stage_done();
+            bd_lo += 4 * kStep;
+            adv2(wi1, wp1);
           }
           op_done();
         }
@@ -304,17 +328,22 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           uint32_t xa_lo = x_lo | b_lbo_x;
           for (int blk = 0; blk < kKC / 2; blk += bott_per_stage) {
             wait_w();
-            uint32_t w_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | b_lbo_bott;
-            for (int u = 0; u < bott_per_stage; ++u) {
-              if (do_mma && elect_one()) {
-                umma_bf16(d_main, stk_desc(xa_lo, desc_hi), stk_desc(w_lo, desc_hi), idesc_bott, (blk + u) > 0);
-                umma_bf16(d_main + (uint32_t)p.bott, stk_desc(xa_lo + 128u, desc_hi), stk_desc(w_lo, desc_hi), idesc_bott, (blk + u) > 0);
+            const uint32_t w_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | b_lbo_bott;
+            if (elect_one()) {
+              uint32_t xa = xa_lo, wl = w_lo;
+              for (int u = 0; u < bott_per_stage; ++u) {
+                if (do_mma) {
+                  umma_bf16(d_main, stk_desc(xa, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
+                  umma_bf16(d_main + (uint32_t)p.bott, stk_desc(xa + 128u, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
+                }
+                xa += kStep;
+                wl += (uint32_t)p.bott * 2u;
               }
-              __syncwarp();
-              xa_lo += kStep;
-              w_lo += (uint32_t)p.bott * 2u;
+              if (!no_w) umma_commit(&wempty[wi]);
             }
-            stage_done();
+            __syncwarp();
+            xa_lo += (uint32_t)bott_per_stage * kStep;
+            if (++wi == kStkStages) { wi = 0; wp ^= 1; }
           }
           op_done();
         }
