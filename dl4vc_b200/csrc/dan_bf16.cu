@@ -405,7 +405,7 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
-// pool[cand][p][c] = mean over reads (fp32)   (model.py:772)
+// pool[cand][c/8][p][c%8] = mean over reads (fp32)   (model.py:772)
 __global__ void pool_mean_bf16_kernel(const uint4* __restrict__ h, long kstride, float* __restrict__ pool, RowGeom g) {
   const int cand = blockIdx.y, kc = blockIdx.z;
   const int pp = blockIdx.x * blockDim.x + threadIdx.x;
@@ -418,9 +418,10 @@ __global__ void pool_mean_bf16_kernel(const uint4* __restrict__ h, long kstride,
 #pragma unroll
     for (int j = 0; j < 8; ++j) s[j] += f[j];
   }
-  float* dst = pool + ((long)cand * g.P + pp) * kC + kc * 8;
-#pragma unroll
-  for (int j = 0; j < 8; ++j) dst[j] = s[j] / (float)g.R;
+  float4* dst = reinterpret_cast<float4*>(pool + (((long)cand * kKC + kc) * g.P + pp) * 8);
+  const float inv = 1.f / (float)g.R;
+  dst[0] = make_float4(s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv);
+  dst[1] = make_float4(s[4] * inv, s[5] * inv, s[6] * inv, s[7] * inv);
 }
 
 // out = bf16(h + pool) on data rows, 0 on gap rows   (model.py:742)
@@ -434,7 +435,7 @@ __global__ void add_pool_bf16_kernel(const uint4* __restrict__ h, const float* _
     if (pp < g.P) {
       float f[8];
       unpack8(v, f);
-      const float4* a = reinterpret_cast<const float4*>(pool + (cand * g.P + pp) * kC + kc * 8);
+      const float4* a = reinterpret_cast<const float4*>(pool + ((cand * kKC + kc) * g.P + pp) * 8);
       const float4 a0 = a[0], a1 = a[1];
       f[0] += a0.x; f[1] += a0.y; f[2] += a0.z; f[3] += a0.w; f[4] += a1.x; f[5] += a1.y; f[6] += a1.z; f[7] += a1.w;
       v = pack8(f);
@@ -808,17 +809,13 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           int l_end = l + 1;
           while (l_end < L && !m->cfg.pool_after[l_end - 1] && l_end - l < kStkMaxSeg) ++l_end;
           const uint4* seg_in = cur;
-          if (l > 0 && m->cfg.pool_after[l - 1]) {
-            uint4* hp = H[(hsel + 2) % 3];
-            { DanProfScope ps(DAN_PROF_POOL, st); add_pool_bf16_kernel<<<grid_for(rows * kKC), 256, 0, st>>>(cur, POOL, hp, pl.kstride, rows, g); }
-            dan_count_launch();
-            seg_in = hp;
-          }
+          const bool with_pool = l > 0 && m->cfg.pool_after[l - 1];      // the pool-add is fused into the segment's load
           uint4* next = H[(hsel + 1) % 3];
           StackParams sp{};
           sp.in = seg_in; sp.in_kstride = pl.kstride; sp.out = next; sp.out_kstride = pl.kstride;
           sp.t_reads_stride = pl.readsPad; sp.num_reads = ns * R; sp.P = P; sp.pitch = g.pitch; sp.bott = bott > 0 ? bott : 32;
           sp.num_layers = l_end - l;
+          sp.pool = with_pool ? POOL : nullptr; sp.reads_per_cand = R;
           for (int k = l; k < l_end; ++k) {
             StackLayer& SL = sp.layer[k - l];
             SL.wstream = bw->wstream[k]; SL.wreplica_stride = bw->wstream_bytes[k]; SL.chan = bw->chan_dev + (size_t)k * 4 * kC; SL.bbias = m->bottB[k];

@@ -57,6 +57,7 @@ struct StackParams {
   uint4* out; long out_kstride;         // chunk-major output rows, 16 planes
   long t_reads_stride;
   int num_reads, P, pitch, bott, num_layers;
+  const float* pool; int reads_per_cand;   // optional read-mean of the previous segment, fp32 [candidate][c/8][p][8]: added to every read on load (model.py:742)
   unsigned long long* prof;            // optional [grid][16] cycle counters (development aid), or null
   uint2* trace; int trace_cap;         // development: event trace of CTA 0 (id, clock), trace[0].x = count
   int debug;                           // development: bit 0 = skip the MMAs, bit 1 = skip epilogue math/stores
@@ -364,7 +365,29 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     // stmatrix / ldmatrix row address of this thread for position group 0: matrix lane>>3 = chunk plane 4q + (lane>>3), row lane&7
     const uint32_t saddr0 = buf_addr + (uint32_t)(4 * q + (lane >> 3)) * kStkPlane + (uint32_t)(kStkLead + (lane & 7)) * 16;
     const int g_begin = h == 0 ? 0 : 14, g_end = h == 0 ? 14 : 26;
+    // x += pool (model.py:734-742: the read-axis mean of the previous layer's output is added to the input of this segment's first
+    // layer). Runs on the freshly loaded read before the slot is handed to the issuer; bf16(x + pool) like the stand-alone kernel.
+    auto add_pool = [&](int read_local, uint32_t parity) {
+      mbar_wait(&sm->in_full[s], parity);
+      const long cand = (long)(r_begin + read_local) / p.reads_per_cand;
+      const float* pl = p.pool + cand * kKC * p.P * 8;
+      uint8_t* b = bufs + (size_t)s * kStkBuf + kStkLead * 16;
+      for (int pos = gtid; pos < p.P; pos += kStkEpiThreads) {
+#pragma unroll 4
+        for (int kc = 0; kc < kKC; ++kc) {
+          uint4* px = reinterpret_cast<uint4*>(b + (size_t)kc * kStkPlane) + pos;
+          const float4* pa = reinterpret_cast<const float4*>(pl + ((long)kc * p.P + pos) * 8);
+          const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1);
+          uint4 v = *px;
+          v.x = pack_bf16x2(bf16_lo(v.x) + a0.x, bf16_hi(v.x) + a0.y); v.y = pack_bf16x2(bf16_lo(v.y) + a0.z, bf16_hi(v.y) + a0.w);
+          v.z = pack_bf16x2(bf16_lo(v.z) + a1.x, bf16_hi(v.z) + a1.y); v.w = pack_bf16x2(bf16_lo(v.w) + a1.z, bf16_hi(v.w) + a1.w);
+          *px = v;
+        }
+      }
+      fence_proxy_async_smem();
+    };
     if (gtid == 0 && s < n_reads) load_read(s);
+    if (p.pool && s < n_reads) add_pool(s, 0);
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
     uint32_t opc = 0, eops = 0;
     int tr_n = 0;
@@ -452,6 +475,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             bulk_wait_read0();
             if (i + 2 < n_reads) load_read(i + 2);
           }
+          if (p.pool && i + 2 < n_reads) add_pool(i + 2, (uint32_t)((i + 2) >> 1) & 1u);
           if (L.highway) mbar_arrive(&sm->act_ready[s]);
           if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 5u << 24 | (eops & 0xFFFFu));
           if (prof) { const long long t1 = clock64(); t_io += t1 - t0; t0 = t1; }
