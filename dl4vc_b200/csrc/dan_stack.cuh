@@ -134,6 +134,10 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
     uint8_t* dst = bufs + (size_t)s * kStkBuf + kStkLead * 16;
     for (int kc = 0; kc < in_kc; ++kc) bulk_g2s(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s]);
+    if (i + 2 < n_reads) {       // the slot's next read: pull it into L2 now so that its load (on the slot's critical path) is an L2 hit
+      const uint4* nxt = src + 2 * (long)p.pitch;
+      for (int kc = 0; kc < in_kc; ++kc) bulk_prefetch_l2(nxt + kc * p.in_kstride, plane_bytes_in);
+    }
   };
 
   // register budget: the producer / issuer warpgroup (warps 16-19) hands registers to the four epilogue warpgroups
@@ -433,6 +437,16 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
         }
         const bool last = l + 1 == p.num_layers;
+        if (last) {
+          // the segment output of this read is final: start writing it back now, under this layer's bottleneck MMA / epilogue
+          named_bar_sync(1 + s, kStkEpiThreads);
+          if (gtid == 0) {
+            uint4* dst = p.out + kLead + (long)(r_begin + i) * p.pitch;
+            const uint8_t* src = bufs + (size_t)s * kStkBuf + kStkLead * 16;
+            for (int kc = 0; kc < kKC; ++kc) bulk_s2g(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in);
+            bulk_commit();
+          }
+        }
         if (L.highway) {
           mbar_wait(&sm->acc_full[s], opc & 1);
           tc_fence_after();
@@ -465,13 +479,9 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           if (prof) { const long long t1 = clock64(); t_bott += t1 - t0; t0 = t1; }
         }
         if (last) {
-          // every MMA and epilogue of this read is done: store the segment output and refill the slot before releasing it
-          named_bar_sync(1 + s, kStkEpiThreads);
+          // every MMA of this read has completed (the last accumulator was awaited above) and the write-back has been issued:
+          // refill the slot as soon as the store has read the buffer
           if (gtid == 0) {
-            uint4* dst = p.out + kLead + (long)(r_begin + i) * p.pitch;
-            const uint8_t* src = bufs + (size_t)s * kStkBuf + kStkLead * 16;
-            for (int kc = 0; kc < kKC; ++kc) bulk_s2g(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in);
-            bulk_commit();
             bulk_wait_read0();
             if (i + 2 < n_reads) load_read(i + 2);
           }

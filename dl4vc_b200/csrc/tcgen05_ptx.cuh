@@ -77,6 +77,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
                ::"r"(smem_u32(smem_dst)), "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// L2 prefetch of a contiguous global range (TMA engine)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // ---- TMEM ----------------------------------------------------------------------------------------------
 template <uint32_t kCols>
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_result) {   // whole warp, .sync.aligned
