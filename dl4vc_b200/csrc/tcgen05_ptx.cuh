@@ -68,6 +68,44 @@ __device__ __forceinline__ void mbar_wait2(uint64_t* a, uint32_t pa, uint64_t* b
   } while (!ok);
 }
 
+// three barriers probed back to back, bounded spin
+__device__ __forceinline__ void mbar_wait3(uint64_t* a, uint32_t pa, uint64_t* b, uint32_t pb, uint64_t* c, uint32_t pc) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p, q, r;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%3], %4;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 r, [%5], %6;\n\t"
+        "and.pred p, p, q;\n\t and.pred p, p, r;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok) : "r"(smem_u32(a)), "r"(pa), "r"(smem_u32(b)), "r"(pb), "r"(smem_u32(c)), "r"(pc) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();
+  } while (!ok);
+}
+
+// six barriers (shared-space addresses) probed back to back, bounded spin. An mbarrier probe costs the issuing warp ~190 cycles
+// even when the phase is already complete (measured, scripts/probes/commit_probe.cu): batching hides all but one of them.
+__device__ __forceinline__ void mbar_wait6(const uint32_t (&bar)[6], const uint32_t (&par)[6]) {
+  uint32_t ok, spins = 0;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p0, p1, p2, p3, p4, p5;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p0, [%1], %7;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p1, [%2], %8;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p2, [%3], %9;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p3, [%4], %10;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p4, [%5], %11;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p5, [%6], %12;\n\t"
+        "and.pred p0, p0, p1;\n\t and.pred p2, p2, p3;\n\t and.pred p4, p4, p5;\n\t and.pred p0, p0, p2;\n\t and.pred p0, p0, p4;\n\t"
+        "selp.u32 %0, 1, 0, p0;\n\t}"
+        : "=r"(ok)
+        : "r"(bar[0]), "r"(bar[1]), "r"(bar[2]), "r"(bar[3]), "r"(bar[4]), "r"(bar[5]),
+          "r"(par[0]), "r"(par[1]), "r"(par[2]), "r"(par[3]), "r"(par[4]), "r"(par[5]) : "memory");
+    if (!ok && ++spins > (1u << 26)) __trap();
+  } while (!ok);
+}
+
 // generic-proxy smem writes -> visible to the async proxy (UMMA operand reads, bulk copies)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -124,6 +162,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 // arrive on an mbarrier when all tcgen05 ops issued so far by this thread have completed
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar_saddr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr) : "memory");
 }
 
 // ---- TMEM -> registers: 32 lanes x 32 consecutive fp32 columns (lane = TMEM datapath lane of this thread) --
