@@ -117,6 +117,7 @@ int dan_model_create(const dan_config* cfg, dan_model** out) {
   m->fcInPad = round_up_i(m->fcIn, 16);
   m->hidden = c.fc_sizes[c.num_fc - 1];
   m->pass_candidates = 64;
+  m->host_mu = new std::mutex();
   *out = m;
   return DAN_OK;
 }
@@ -125,6 +126,12 @@ int dan_model_destroy(dan_model* m) {
   if (!m) return DAN_OK;
   dan_fp32_free(m);
   dan_bf16_free(m);
+  if (m->copy_stream) {
+    cudaStreamDestroy(m->copy_stream);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(m->ev_copied[i]); cudaEventDestroy(m->ev_done[i]); }
+    cudaEventDestroy(m->ev_entry);
+  }
+  delete m->host_mu;
   delete m;
   return DAN_OK;
 }
@@ -182,14 +189,22 @@ int dan_forward(dan_model* m, int precision, const uint8_t* reads, const uint8_t
   return dan_fp32_forward(m, in, batch, heads_out, workspace, workspace_bytes, st);
 }
 
-static size_t host_stage_bytes(const dan_model* m, int batch) {
-  const size_t tile = (size_t)batch * m->P * m->R, vec = (size_t)batch * m->P;
-  return 3 * round_up_z(tile, 256) + 3 * round_up_z(vec, 256) + round_up_z((size_t)batch * DAN_NUM_HEAD_OUTPUTS * 4, 256);
+// ---- host-buffer entry point: chunked, double-buffered H2D staging on a side stream (north_star item 4) -------------------
+// The batch is cut into chunks of kHostChunk candidates. Chunk k+1 is copied from the caller's (pinned) host buffers into staging
+// buffer (k+1)&1 on the model's copy stream while chunk k runs on the caller's stream; events order copy -> compute and
+// compute -> reuse of the staging buffer. Only the first chunk's copy is exposed.
+static const int kHostChunk = 512;
+static int host_chunk(int batch) { return batch < kHostChunk ? (batch > 0 ? batch : 1) : kHostChunk; }
+static size_t host_stage_bytes_chunk(const dan_model* m, int chunk) {
+  const size_t tile = (size_t)chunk * m->P * m->R, vec = (size_t)chunk * m->P;
+  return 3 * round_up_z(tile, 256) + 3 * round_up_z(vec, 256);
 }
 
 size_t dan_workspace_bytes_host(const dan_model* m, int batch, int precision) {
   if (!m || batch < 0) return 0;
-  return round_up_z(dan_workspace_bytes(m, batch, precision), 256) + host_stage_bytes(m, batch);
+  const int chunk = host_chunk(batch);
+  return round_up_z(dan_workspace_bytes(m, chunk, precision), 256) + 2 * host_stage_bytes_chunk(m, chunk) +
+         round_up_z((size_t)(batch > 0 ? batch : 1) * DAN_NUM_HEAD_OUTPUTS * 4, 256);
 }
 
 int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
@@ -199,26 +214,55 @@ int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const ui
   int rc = check_forward_args(m, precision, reads, q_scores, strands, ref, ref_masks, var_masks, batch, heads_out_host);
   if (rc) return rc;
   if (batch == 0) return DAN_OK;
-  const size_t core = round_up_z(dan_workspace_bytes(m, batch, precision), 256);
-  if (!workspace || workspace_bytes < core + host_stage_bytes(m, batch)) { dan_set_error("workspace too small for host staging"); return DAN_E_WORKSPACE; }
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  char* p = static_cast<char*>(workspace) + core;
-  const size_t tile = (size_t)batch * m->P * m->R, vec = (size_t)batch * m->P;
-  auto stage = [&](const uint8_t* src, size_t n) -> uint8_t* {
-    uint8_t* d = reinterpret_cast<uint8_t*>(p);
-    p += round_up_z(n, 256);
-    if (!src) return nullptr;
-    cudaMemcpyAsync(d, src, n, cudaMemcpyHostToDevice, st);
-    return d;
-  };
-  DevInputs in{};
-  in.reads = stage(reads, tile); in.q = stage(q_scores, tile); in.strands = stage(strands, tile);
-  in.ref = stage(ref, vec); in.ref_masks = stage(ref_masks, vec); in.var_masks = stage(var_masks, vec);
-  float* dheads = reinterpret_cast<float*>(p);
-  DAN_CUDA_TRY(cudaGetLastError());
-  if (precision == DAN_PRECISION_BF16) rc = dan_bf16_forward(m, in, batch, dheads, workspace, core, st);
-  else rc = dan_fp32_forward(m, in, batch, dheads, workspace, core, st);
-  if (rc) return rc;
+  const int chunk = host_chunk(batch);
+  const size_t core = round_up_z(dan_workspace_bytes(m, chunk, precision), 256);
+  const size_t stage_b = host_stage_bytes_chunk(m, chunk);
+  if (!workspace || workspace_bytes < dan_workspace_bytes_host(m, batch, precision)) { dan_set_error("workspace too small for host staging"); return DAN_E_WORKSPACE; }
+  std::lock_guard<std::mutex> lk(*m->host_mu);          // the copy stream and its events belong to the model handle
+  if (!m->copy_stream) {
+    DAN_CUDA_TRY(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      DAN_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_copied[i], cudaEventDisableTiming));
+      DAN_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_done[i], cudaEventDisableTiming));
+    }
+    DAN_CUDA_TRY(cudaEventCreateWithFlags(&m->ev_entry, cudaEventDisableTiming));
+  }
+  cudaStream_t st = static_cast<cudaStream_t>(stream), cs = m->copy_stream;
+  char* base = static_cast<char*>(workspace);
+  char* stage_base[2] = {base + core, base + core + stage_b};
+  float* dheads = reinterpret_cast<float*>(base + core + 2 * stage_b);
+  const size_t tile1 = (size_t)m->P * m->R, vec1 = (size_t)m->P;
+  // staging buffers may still be read by work queued earlier on the caller's stream
+  DAN_CUDA_TRY(cudaEventRecord(m->ev_entry, st));
+  DAN_CUDA_TRY(cudaStreamWaitEvent(cs, m->ev_entry, 0));
+  const int nchunks = (batch + chunk - 1) / chunk;
+  int launches = 0;
+  for (int k = 0; k < nchunks; ++k) {
+    const int c0 = k * chunk, nb = batch - c0 < chunk ? batch - c0 : chunk, b = k & 1;
+    if (k >= 2) DAN_CUDA_TRY(cudaStreamWaitEvent(cs, m->ev_done[b], 0));          // chunk k-2 has finished with this staging buffer
+    char* p = stage_base[b];
+    auto stage = [&](const uint8_t* src, size_t per_cand) -> const uint8_t* {
+      uint8_t* d = reinterpret_cast<uint8_t*>(p);
+      p += round_up_z((size_t)chunk * per_cand, 256);
+      if (!src) return nullptr;
+      cudaMemcpyAsync(d, src + (size_t)c0 * per_cand, (size_t)nb * per_cand, cudaMemcpyHostToDevice, cs);
+      return d;
+    };
+    DevInputs in{};
+    in.reads = stage(reads, tile1); in.q = stage(q_scores, tile1); in.strands = stage(strands, tile1);
+    in.ref = stage(ref, vec1); in.ref_masks = stage(ref_masks, vec1); in.var_masks = stage(var_masks, vec1);
+    DAN_CUDA_TRY(cudaGetLastError());
+    DAN_CUDA_TRY(cudaEventRecord(m->ev_copied[b], cs));
+    DAN_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_copied[b], 0));
+    float* out = dheads + (size_t)c0 * DAN_NUM_HEAD_OUTPUTS;
+    g_launches = 0;
+    if (precision == DAN_PRECISION_BF16) rc = dan_bf16_forward(m, in, nb, out, workspace, core, st);
+    else rc = dan_fp32_forward(m, in, nb, out, workspace, core, st);
+    if (rc) return rc;
+    launches += g_launches;
+    DAN_CUDA_TRY(cudaEventRecord(m->ev_done[b], st));
+  }
+  g_launches = launches;
   DAN_CUDA_TRY(cudaMemcpyAsync(heads_out_host, dheads, (size_t)batch * DAN_NUM_HEAD_OUTPUTS * 4, cudaMemcpyDeviceToHost, st));
   return DAN_OK;
 }

@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <mutex>
 #include "../../include/dan_b200.h"
 
 #define DAN_VOCAB 10
@@ -77,6 +78,9 @@ struct dan_model {
   float* headW; float* headB;     // [hidden][32], [32]
   // ---- bf16 packed weights for the tcgen05 path (see dan_bf16.cu) ----
   void* bf16_store;               // opaque Bf16Weights*
+  // ---- dan_forward_host: side stream + events for the double-buffered H2D staging ----
+  cudaStream_t copy_stream; cudaEvent_t ev_copied[2], ev_done[2], ev_entry;
+  std::mutex* host_mu;
 };
 
 // fp32 path (dan_fp32.cu)

@@ -366,6 +366,47 @@ class Basic2DNet(nn.Module):
             self.last_launch_count = lib.dan_last_launch_count()
         return out
 
+    def forward_heads_host(self, reads, ref, q_scores=None, strands=None, ref_masks=None, var_masks=None, out=None):
+        """Host-buffer variant of forward_heads: uint8 CPU tensors (pinned for true asynchrony) in, (B,27) fp32 CPU tensor out.
+        The library cuts the batch into chunks and overlaps the H2D copy of chunk k+1 (side stream) with the kernels of chunk k
+        (dan_forward_host). Asynchronous on the current stream: synchronize it before reading `out`."""
+        if self.training:
+            raise NotImplementedError("dl4vc_b200.Basic2DNet: training-mode forward is not implemented; call .eval()")
+        dev = self._device()
+        lib = _lib.load_library()
+
+        def host_u8(t, used=True):
+            if t is None or not used:
+                return None
+            if t.device.type != "cpu":
+                raise RuntimeError("forward_heads_host takes CPU tensors; use forward_heads for device tensors")
+            if t.dtype != torch.uint8:
+                t = t.to(torch.uint8)
+            return t.contiguous()
+
+        with torch.cuda.device(dev):
+            st = self._state(dev)
+            prec = _PRECISIONS[self.precision]
+            B = int(reads.shape[0])
+            P, R = self.single_read_len, self.num_single_reads
+            if tuple(reads.shape[1:]) != (P, R):
+                raise RuntimeError(f"reads must be (batch, {P}, {R}) [batch, position, read] (dataset.py:672-680), got {tuple(reads.shape)}")
+            r8, f8 = host_u8(reads), host_u8(ref)
+            q8, s8 = host_u8(q_scores, self.use_q_scores), host_u8(strands, self.use_strands)
+            rm8, vm8 = host_u8(ref_masks, self.use_reads_ref_var_mask), host_u8(var_masks, self.use_reads_ref_var_mask)
+            if out is None:
+                out = torch.empty((B, _lib.NUM_HEAD_OUTPUTS), dtype=torch.float32).pin_memory()
+            if B == 0:
+                return out
+            ws = self._workspace(st, dev, B, prec, host=True)
+            p = lambda t: None if t is None else t.data_ptr()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            self._host_keepalive = (r8, f8, q8, s8, rm8, vm8, out)          # the copies are asynchronous
+            _lib.check(lib.dan_forward_host(st.handle, prec, p(r8), p(q8), p(s8), p(f8), p(rm8), p(vm8), B, out.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), stream), "dan_forward_host")
+            self.last_launch_count = lib.dan_last_launch_count()
+        return out
+
     def forward(self, reads, ref, q_scores, strands, binary_trust_vector,
                 af_scores, ref_bases, var_bases, ref_masks, var_masks,
                 rm_non_var_reads=0, rm_var_reads=0, debug=False):
