@@ -193,7 +193,8 @@ int dan_forward(dan_model* m, int precision, const uint8_t* reads, const uint8_t
 // The batch is cut into chunks of kHostChunk candidates. Chunk k+1 is copied from the caller's (pinned) host buffers into staging
 // buffer (k+1)&1 on the model's copy stream while chunk k runs on the caller's stream; events order copy -> compute and
 // compute -> reuse of the staging buffer. Only the first chunk's copy is exposed.
-static const int kHostChunk = 512;
+static const int kHostChunk = 1024;   // = the FC trunk's chunk: the 151 MB FC1 weight stream is read once per 1024 candidates either way
+static const int kHostFirst = 128;
 static int host_chunk(int batch) { return batch < kHostChunk ? (batch > 0 ? batch : 1) : kHostChunk; }
 static size_t host_stage_bytes_chunk(const dan_model* m, int chunk) {
   const size_t tile = (size_t)chunk * m->P * m->R, vec = (size_t)chunk * m->P;
@@ -235,10 +236,11 @@ int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const ui
   // staging buffers may still be read by work queued earlier on the caller's stream
   DAN_CUDA_TRY(cudaEventRecord(m->ev_entry, st));
   DAN_CUDA_TRY(cudaStreamWaitEvent(cs, m->ev_entry, 0));
-  const int nchunks = (batch + chunk - 1) / chunk;
+  // the first chunk is small (its copy is the only one that is not hidden), the rest are full FC-sized chunks
+  const int first = batch > 2 * kHostFirst ? kHostFirst : chunk;
   int launches = 0;
-  for (int k = 0; k < nchunks; ++k) {
-    const int c0 = k * chunk, nb = batch - c0 < chunk ? batch - c0 : chunk, b = k & 1;
+  for (int k = 0, c0 = 0; c0 < batch; ++k) {
+    const int want = k == 0 ? first : chunk, nb = batch - c0 < want ? batch - c0 : want, b = k & 1;
     if (k >= 2) DAN_CUDA_TRY(cudaStreamWaitEvent(cs, m->ev_done[b], 0));          // chunk k-2 has finished with this staging buffer
     char* p = stage_base[b];
     auto stage = [&](const uint8_t* src, size_t per_cand) -> const uint8_t* {
@@ -261,6 +263,7 @@ int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const ui
     if (rc) return rc;
     launches += g_launches;
     DAN_CUDA_TRY(cudaEventRecord(m->ev_done[b], st));
+    c0 += nb;
   }
   g_launches = launches;
   DAN_CUDA_TRY(cudaMemcpyAsync(heads_out_host, dheads, (size_t)batch * DAN_NUM_HEAD_OUTPUTS * 4, cudaMemcpyDeviceToHost, st));

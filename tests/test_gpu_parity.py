@@ -133,11 +133,11 @@ def test_bf16_matches_fp32_path_on_a_larger_batch():
 
 def test_host_path_matches_device_path_across_chunks():
     """dan_forward_host (chunked, double-buffered H2D on a side stream) returns exactly what dan_forward returns on resident inputs;
-    1100 candidates = three staging chunks (512 + 512 + 76), pinned and pageable host tensors."""
+    2100 candidates = staging chunks of 128 + 1024 + 948, pinned and pageable host tensors."""
     cfg = small_config()
     sd = synth_state_dict(cfg, seed=9)
     base = make_pileups(100, seed=321, coverage="poisson")
-    arrays = [np.concatenate([a] * 11, axis=0) for a in base.arrays()]
+    arrays = [np.concatenate([a] * 21, axis=0) for a in base.arrays()]
     model = build_model(cfg, sd, precision="bf16")
     want = _heads(model, arrays)
     r, q, s, ref, rm, vm = _tensors(arrays)
@@ -150,4 +150,4 @@ def test_host_path_matches_device_path_across_chunks():
     assert np.array_equal(again.numpy(), want)
     # rows repeat with period 100: candidates are independent of their position in the batch / chunk (up to the summation
     # order of the split-K highway GEMM, which uses fp32 atomics when a pass has few tiles)
-    assert rel_err(want[1000:1100], want[:100]) < 1e-3
+    assert rel_err(want[2000:2100], want[:100]) < 1e-3
