@@ -16,7 +16,7 @@ worst case). Candidates are independent, so N GPUs shard by candidate with no co
             the reference's own torch-CPU op sequence (oracle/dan_torch_cpu.py — the reference is pure PyTorch and
             /root/reference does not exist on the GPU box) on all host cores, bounded sample of the same workload
 
-The per-step batch (default 4096 candidates = 249 MB of uint8 input) is larger than the 126 MB L2, so no L2 flush is
+The per-step batch (default 4144 candidates = 252 MB of uint8 input) is larger than the 126 MB L2, so no L2 flush is
 needed between timed iterations.
 """
 from __future__ import annotations
@@ -330,7 +330,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--batch", type=int, default=4096, help="candidates per step per GPU")
+    ap.add_argument("--batch", type=int, default=4144, help="candidates per step per GPU (28 passes of 148 candidates)")
     ap.add_argument("--pass-candidates", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

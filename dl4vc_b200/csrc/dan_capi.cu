@@ -116,7 +116,7 @@ int dan_model_create(const dan_config* cfg, dan_model** out) {
   m->fcIn = (c.pool_combine_dimension > 0 ? c.pool_combine_dimension : m->pooled) + m->hwFeat;
   m->fcInPad = round_up_i(m->fcIn, 16);
   m->hidden = c.fc_sizes[c.num_fc - 1];
-  m->pass_candidates = 64;
+  m->pass_candidates = 148;    // 148 candidates x 100 reads = 100 reads per CTA of the persistent stack kernel on a 148-SM B200: no tail imbalance
   m->host_mu = new std::mutex();
   *out = m;
   return DAN_OK;
