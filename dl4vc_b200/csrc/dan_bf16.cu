@@ -834,10 +834,13 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           { DanProfScope ps(DAN_PROF_CONV_STACK, st);
             if (sp.trace) dan_stack_kernel<3><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);                  // development builds of the kernel
             else if (sp.prof) dan_stack_kernel<2><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);
-            else if (sp.debug) dan_stack_kernel<1><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);
+            else if (sp.debug & ~64) dan_stack_kernel<1><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);
             else dan_stack_kernel<0><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp); }
           dan_count_launch();
           DAN_CUDA_TRY(cudaGetLastError());
+          static const bool sync_dbg = getenv("DAN_B200_SYNC") != nullptr;          // development: find the launch that hangs / faults
+          if (sync_dbg) { fprintf(stderr, "[sync] stack layers %d-%d reads %d grid %d pool %d ... ", l + 1, l_end, sp.num_reads, grid, sp.pool != nullptr); fflush(stderr);
+                          cudaError_t e = cudaStreamSynchronize(st); fprintf(stderr, "%s\n", cudaGetErrorString(e)); fflush(stderr); }
           if (sp.trace) {
             std::vector<uint2> h(sp.trace_cap);
             DAN_CUDA_TRY(cudaStreamSynchronize(st));
