@@ -159,14 +159,19 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     // ===================== weight producer: ONE stream for both slots. The two reads of a pair go through the same op
     // sequence one op apart (see the issuers), so every stage is consumed twice before it is refilled: the L2 -> SMEM
     // weight traffic (the binding resource of this kernel when each slot streamed its own copy) is halved. =========
-    if (warp == 16 && lane == 0 && !(kDev != 0 && (p.debug & 16))) {
-      uint32_t idx = 0, par = 1;     // first pass over the ring: the "empty" phase counts as complete
+    // Two producer threads (lane 0 of warps 16 and 17) take alternate stages of the stream: one thread needs ~300 cycles per
+    // stage (empty-barrier probe + expect_tx + copy issue), which is close to the rate at which the tensor pipe drains a stage.
+    if (lane == 0 && !(kDev != 0 && (p.debug & 16))) {
+      const uint32_t mine = (uint32_t)(warp - 16);
+      uint32_t idx = 0, par = 1, seq = 0;     // first pass over the ring: the "empty" phase counts as complete
       auto emit = [&](const uint8_t* src, uint32_t bytes) {
         for (uint32_t off = 0; off < bytes; off += kStkStageBytes) {
-          const uint32_t n = min((uint32_t)kStkStageBytes, bytes - off);
-          mbar_wait(&sm->w_empty[idx], par);
-          mbar_expect_tx(&sm->w_full[idx], n);
-          bulk_g2s(rings + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[idx]);
+          if ((seq++ & 1u) == mine) {
+            const uint32_t n = min((uint32_t)kStkStageBytes, bytes - off);
+            mbar_wait(&sm->w_empty[idx], par);
+            mbar_expect_tx(&sm->w_full[idx], n);
+            bulk_g2s(rings + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[idx]);
+          }
           if (++idx == kStkStages) { idx = 0; par ^= 1; }
         }
       };
