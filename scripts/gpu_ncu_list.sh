@@ -2,9 +2,9 @@
 # ncu launch list (per-launch gpu__time_duration) of one small bench step; the bench itself is run first without ncu.
 set -u
 mkdir -p gpurun_out
-B=${BATCH:-128}
+B=${BATCH:-296}
 python bench.py --steps 1 --warmup 1 --batch $B --no-cpu-baseline > gpurun_out/bench_small.json 2> gpurun_out/bench_small.err || exit 1
-ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-200} -c ${COUNT:-400} --csv --log-file gpurun_out/launches.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s ${SKIP:-60} -c ${COUNT:-120} --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 1 --warmup 1 --batch $B --no-cpu-baseline > gpurun_out/ncu_launches.log 2>&1
 echo "ncu rc=$?"
 python - <<'PY'
