@@ -1,0 +1,123 @@
+"""Host-side feeder and score post-processing around the DAN forward (north_star item 4).
+
+PinnedBatchFeeder  collates the loader's per-candidate dicts (the schema `dl4vc/dataset.py:672-680` yields: uint8 `reads`,
+                   `q-scores`, `strands` of shape (201, 100), `ref`, `ref_mask`, `var_mask` of shape (201,)) straight into
+                   rotating PINNED uint8 batch buffers — no int64 inflation (`trainer.py:520-528` moves 8x the bytes) — and
+                   hands them to `Basic2DNet.forward_heads_host`, whose library side overlaps the H2D staging of a chunk
+                   with the kernels of the previous one. Collating batch k+1 on the host overlaps the GPU work of batch k.
+scores_from_heads  the caller-side post-ops of `trainer.py:611-623`: softmax over xbinary / xVT and the variant score 1 - p0.
+format_vcf_info    the `BP=..;NV=..;HV=..;OV=..` field `utils.append_vcf_records` splices into VCF column 3 (`utils.py:162-178`).
+"""
+from __future__ import annotations
+
+from collections import deque
+
+import numpy as np
+import torch
+
+ITEM_KEYS = (("reads", "reads"), ("q-scores", "q"), ("strands", "strands"), ("ref", "ref"), ("ref_mask", "ref_masks"),
+             ("var_mask", "var_masks"))
+
+
+class HostBatch:
+    """One pinned (when CUDA is available) uint8 batch in the layout the C-ABI takes: [batch][position][read]."""
+
+    def __init__(self, capacity: int, read_len: int = 201, num_reads: int = 100, pin: bool | None = None):
+        pin = torch.cuda.is_available() if pin is None else pin
+        mk = lambda *shape: (torch.empty(shape, dtype=torch.uint8).pin_memory() if pin else torch.empty(shape, dtype=torch.uint8))
+        self.reads, self.q, self.strands = (mk(capacity, read_len, num_reads) for _ in range(3))
+        self.ref, self.ref_masks, self.var_masks = (mk(capacity, read_len) for _ in range(3))
+        self.capacity, self.size = capacity, 0
+        self.meta = []
+
+    def fill(self, items) -> "HostBatch":
+        """Copy a list of dataset items into the buffers (values are 0..93, any integer dtype narrows losslessly)."""
+        n = len(items)
+        if n > self.capacity:
+            raise ValueError(f"{n} items > capacity {self.capacity}")
+        views = {"reads": self.reads.numpy(), "q": self.q.numpy(), "strands": self.strands.numpy(), "ref": self.ref.numpy(),
+                 "ref_masks": self.ref_masks.numpy(), "var_masks": self.var_masks.numpy()}
+        for i, it in enumerate(items):
+            for key, dst in ITEM_KEYS:
+                a = np.asarray(it[key])
+                if a.shape != views[dst].shape[1:]:
+                    raise ValueError(f"item {i}: '{key}' has shape {a.shape}, expected {views[dst].shape[1:]} (dataset.py:672-680)")
+                views[dst][i] = a          # numpy casts to uint8
+        self.size = n
+        self.meta = [(it.get("name"), it.get("vcfrec")) for it in items]
+        return self
+
+    def tensors(self):
+        n = self.size
+        return self.reads[:n], self.ref[:n], self.q[:n], self.strands[:n], self.ref_masks[:n], self.var_masks[:n]
+
+
+class PinnedBatchFeeder:
+    """submit(items) -> pending result; results() yields (meta, heads[n, 27]) in submission order.
+
+    `depth` host batches rotate: while the GPU works on batch k (asynchronously, on `stream`), batch k+1 is collated into the
+    next pinned buffer. A buffer is reused only after its result has been consumed, so at most `depth` batches are in flight."""
+
+    def __init__(self, model, batch_size: int, depth: int = 2, stream: torch.cuda.Stream | None = None):
+        self.model, self.batch_size, self.depth = model, batch_size, depth
+        self.stream = stream
+        self.free = deque(HostBatch(batch_size, model.single_read_len, model.num_single_reads) for _ in range(depth))
+        self.pending = deque()
+
+    def submit(self, items):
+        if not self.free:
+            raise RuntimeError("all host batches are in flight: consume results() first")
+        hb = self.free.popleft().fill(items)
+        ctx = torch.cuda.stream(self.stream) if self.stream is not None else _null()
+        with ctx:
+            out = self.model.forward_heads_host(*hb.tensors())
+            ev = torch.cuda.Event()
+            ev.record()
+        self.pending.append((hb, out, ev))
+
+    def results(self, drain: bool = True):
+        """Yield finished (meta, heads) pairs; with drain=True waits for everything submitted so far."""
+        while self.pending and (drain or self.pending[0][2].query()):
+            hb, out, ev = self.pending.popleft()
+            ev.synchronize()
+            heads = out[: hb.size].clone()
+            meta = hb.meta
+            self.free.append(hb)
+            yield meta, heads
+
+
+class _null:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
+
+
+def scores_from_heads(heads: torch.Tensor):
+    """(B,27) head matrix -> (bin_score (B,), vt_probs (B,3)) exactly as trainer.test computes them (trainer.py:611-623,
+    use_var_type_threshold off): bin_score = 1 - softmax(xbinary)[:,0]; vt_probs = softmax(xVT) = P{no variant, het, hom}."""
+    xbinary, xvt = heads[:, 0:2], heads[:, 2:5]
+    bin_score = 1.0 - torch.softmax(xbinary, dim=1)[:, 0]
+    return bin_score, torch.softmax(xvt, dim=1)
+
+
+def format_vcf_info(bin_score, vt_probs):
+    """The strings utils.append_vcf_records writes into VCF column 3 (utils.py:171-176), vectorised over the batch."""
+    b = np.asarray(bin_score, dtype=np.float64)
+    v = np.asarray(vt_probs, dtype=np.float64)
+    return ["BP=%.8f;NV=%.8f;HV=%.8f;OV=%.8f" % (b[i], v[i, 0], v[i, 1], v[i, 2]) for i in range(len(b))]
+
+
+def splice_vcf_records(vcf_records, bin_score, vt_probs):
+    """Records with the score field spliced in, one per line, as append_vcf_records would append them (utils.py:166-178)."""
+    info = format_vcf_info(bin_score, vt_probs)
+    if len(info) != len(vcf_records):
+        raise AssertionError("mis-match between results and VCF to save")          # utils.py:165
+    out = []
+    for rec, txt in zip(vcf_records, info):
+        items = rec.strip().split("\t")
+        assert items[2] == ".", "DANGER -- would replace non-empty INFO -- check the hack"   # utils.py:172
+        items[2] = txt
+        out.append("\t".join(items))
+    return out

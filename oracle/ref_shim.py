@@ -60,6 +60,14 @@ def import_reference():
     return create_arg_parser, Basic2DNet
 
 
+def import_reference_module(name: str):
+    """Import another module of the reference tree (e.g. 'dl4vc.utils') under the same stubs."""
+    import importlib
+
+    import_reference()
+    return importlib.import_module(name)
+
+
 def build_reference_model(cfg, state_dict=None, quiet=True):
     """Construct the reference Basic2DNet the way main.py:99-112 does and optionally load weights."""
     create_arg_parser, Basic2DNet = import_reference()

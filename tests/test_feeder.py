@@ -1,0 +1,61 @@
+"""CPU: host logic either side of the hot path — collation of dataset items into uint8 batches, the trainer's score post-ops and
+the VCF INFO field, checked against the reference's own functions where they can be imported."""
+import numpy as np
+import pytest
+import torch
+
+from dl4vc_b200.feeder import HostBatch, scores_from_heads, format_vcf_info, splice_vcf_records
+from dl4vc_b200.synth import make_pileups
+from oracle import ref_shim
+
+
+def _items(batch):
+    out = []
+    for i in range(len(batch.reads)):
+        out.append({"reads": batch.reads[i].astype(np.int64), "q-scores": batch.q_scores[i], "strands": batch.strands[i], "ref": batch.ref[i],
+                    "ref_mask": batch.ref_masks[i], "var_mask": batch.var_masks[i], "name": "chr1:%d" % i,
+                    "vcfrec": "chr1\t%d\t.\tA\tT\t.\t.\t.\tGT\t0/1" % (1000 + i)})
+    return out
+
+
+def test_host_batch_collates_dataset_items_losslessly():
+    b = make_pileups(5, seed=3, coverage="poisson")
+    hb = HostBatch(8, pin=False).fill(_items(b))
+    r, ref, q, s, rm, vm = hb.tensors()
+    assert r.dtype == torch.uint8 and tuple(r.shape) == (5, 201, 100)
+    assert np.array_equal(r.numpy(), b.reads) and np.array_equal(q.numpy(), b.q_scores) and np.array_equal(s.numpy(), b.strands)
+    assert np.array_equal(ref.numpy(), b.ref) and np.array_equal(rm.numpy(), b.ref_masks) and np.array_equal(vm.numpy(), b.var_masks)
+    assert hb.meta[4][0] == "chr1:4"
+    with pytest.raises(ValueError):
+        HostBatch(2, pin=False).fill(_items(b))
+    bad = _items(b)[:1]
+    bad[0]["reads"] = bad[0]["reads"].T
+    with pytest.raises(ValueError):
+        HostBatch(2, pin=False).fill(bad)
+
+
+def test_scores_match_trainer_post_ops():
+    g = torch.Generator().manual_seed(0)
+    heads = torch.randn(17, 27, generator=g) * 3
+    bin_score, vt = scores_from_heads(heads)
+    # trainer.py:617-623
+    want_bin = 1.0 - torch.nn.functional.softmax(heads[:, 0:2], dim=1)[:, 0]
+    want_vt = torch.nn.functional.softmax(heads[:, 2:5], dim=1)
+    assert torch.equal(bin_score, want_bin) and torch.equal(vt, want_vt)
+    assert torch.allclose(vt.sum(1), torch.ones(17), atol=1e-6)
+
+
+def test_vcf_info_field_matches_reference_writer(tmp_path):
+    b = np.array([0.25, 0.99999999]); v = np.array([[0.75, 0.125, 0.125], [1e-9, 0.5, 0.5]])
+    recs = ["chr1\t100\t.\tA\tT\t.\t.\t.\tGT\t0/1\n", "chr2\t200\t.\tG\tGA\t.\t.\t.\tGT\t1/1"]
+    lines = splice_vcf_records(recs, b, v)
+    assert lines[0].split("\t")[2] == "BP=0.25000000;NV=0.75000000;HV=0.12500000;OV=0.12500000"
+    assert format_vcf_info(b, v)[1] == "BP=0.99999999;NV=0.00000000;HV=0.50000000;OV=0.50000000"
+    with pytest.raises(AssertionError):
+        splice_vcf_records(["chr1\t100\trs1\tA\tT"], b[:1], v[:1])
+    if ref_shim.reference_available():
+        utils = ref_shim.import_reference_module("dl4vc.utils")
+        f = tmp_path / "out.vcf"
+        f.write_text("")
+        utils.append_vcf_records(str(f), list(b), list(v), recs)
+        assert f.read_text().splitlines() == lines
