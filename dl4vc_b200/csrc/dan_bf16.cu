@@ -405,14 +405,31 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
   return make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
 }
 
+// loads in flight per thread of the pooling kernels: they run as one 64-thread CTA per SM beside the persistent stack kernel
+// (4096 spare registers per SM), so memory-level parallelism has to come from the thread itself
+constexpr int kPoolUnroll = 8;
+
 // pool[cand][c/8][p][c%8] = mean over reads (fp32)   (model.py:772)
-__global__ void pool_mean_bf16_kernel(const uint4* __restrict__ h, long kstride, float* __restrict__ pool, RowGeom g) {
+__global__ void __launch_bounds__(64) pool_mean_bf16_kernel(const uint4* __restrict__ h, long kstride, float* __restrict__ pool, RowGeom g) {
   const int cand = blockIdx.y, kc = blockIdx.z;
   const int pp = blockIdx.x * blockDim.x + threadIdx.x;
   if (pp >= g.P) return;
   float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const uint4* src = h + kc * kstride + kLead + (long)cand * g.R * g.pitch + pp;
-  for (int r = 0; r < g.R; ++r) {
+  int r = 0;
+  for (; r + kPoolUnroll <= g.R; r += kPoolUnroll) {
+    uint4 v[kPoolUnroll];
+#pragma unroll
+    for (int u = 0; u < kPoolUnroll; ++u) v[u] = __ldg(src + (long)(r + u) * g.pitch);
+#pragma unroll
+    for (int u = 0; u < kPoolUnroll; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s[j] += f[j];
+    }
+  }
+  for (; r < g.R; ++r) {
     float f[8];
     unpack8(__ldg(src + (long)r * g.pitch), f);
 #pragma unroll
@@ -445,7 +462,7 @@ __global__ void add_pool_bf16_kernel(const uint4* __restrict__ h, const float* _
 }
 
 // final max ‖ mean over reads -> FC input pieces (bf16 feature order: max p*C+c | mean P*C+p*C+c)
-__global__ void pool_final_bf16_kernel(const uint4* __restrict__ h, long kstride, uint4* __restrict__ fcin, long fc_kstride,
+__global__ void __launch_bounds__(64) pool_final_bf16_kernel(const uint4* __restrict__ h, long kstride, uint4* __restrict__ fcin, long fc_kstride,
                                        int cand0, RowGeom g, int skip_max) {
   const int cand = blockIdx.y, kc = blockIdx.z;
   const int pp = blockIdx.x * blockDim.x + threadIdx.x;
@@ -454,7 +471,20 @@ __global__ void pool_final_bf16_kernel(const uint4* __restrict__ h, long kstride
 #pragma unroll
   for (int j = 0; j < 8; ++j) mx[j] = -INFINITY;
   const uint4* src = h + kc * kstride + kLead + (long)cand * g.R * g.pitch + pp;
-  for (int r = 0; r < g.R; ++r) {
+  int r = 0;
+  for (; r + kPoolUnroll <= g.R; r += kPoolUnroll) {
+    uint4 v[kPoolUnroll];
+#pragma unroll
+    for (int u = 0; u < kPoolUnroll; ++u) v[u] = __ldg(src + (long)(r + u) * g.pitch);
+#pragma unroll
+    for (int u = 0; u < kPoolUnroll; ++u) {
+      float f[8];
+      unpack8(v[u], f);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s[j] += f[j]; mx[j] = fmaxf(mx[j], f[j]); }
+    }
+  }
+  for (; r < g.R; ++r) {
     float f[8];
     unpack8(__ldg(src + (long)r * g.pitch), f);
 #pragma unroll
@@ -565,6 +595,8 @@ struct Bf16Weights {
   // host copies of the per-channel epilogue constants (kernel parameters -> constant bank)
   float bias[DAN_MAX_LAYERS][kC], scale[DAN_MAX_LAYERS][kC], shift[DAN_MAX_LAYERS][kC], rbias[DAN_MAX_LAYERS][kC], bbias[DAN_MAX_LAYERS][64];
   int num_sms;
+  // software pipeline across passes (dan_bf16_forward): side stream for the read-axis pooling kernels + ordering events
+  cudaStream_t side; cudaEvent_t ev_seg1[2], ev_pm[2], ev_seg2[2], ev_pf[2], ev_comp[2], ev_hw[2], ev_side;
 };
 
 inline int grid_for(long total, int block = 256) {
@@ -580,7 +612,7 @@ struct Bf16Plan {
   long hw_layer_stride;
   long t_layer_pieces;               // uint4 pieces of one layer's T matrix
   int fcKC;                          // FC input pieces
-  size_t off_zero_begin, off_x0, off_h[3], off_zero_end, off_t, off_pool, off_agree, off_hw, off_fcin, off_fcx[DAN_MAX_FC], total;
+  size_t off_zero_begin, off_x0, off_h[4], off_zero_end, off_t[2], off_pool[2], off_agree, off_hw[2], off_fcin, off_fcx[DAN_MAX_FC], total;
   int maxN;
 };
 
@@ -598,15 +630,15 @@ Bf16Plan make_plan(const dan_model* m, int batch) {
   auto take = [&](size_t bytes) { size_t o = off; off += round_up_z(bytes, 1024); return o; };
   pl.off_zero_begin = off;
   pl.off_x0 = take((size_t)(m->CinPad / 8) * pl.kstride * 16);
-  for (int i = 0; i < 3; ++i) pl.off_h[i] = take((size_t)kKC * pl.kstride * 16);
+  for (int i = 0; i < 4; ++i) pl.off_h[i] = take((size_t)kKC * pl.kstride * 16);     // 3 rotate on the sequential path; 2 + 2 on the pipelined one
   pl.off_zero_end = off;
   const int bott = m->bott > 0 ? m->bott : 32;
   pl.t_layer_pieces = (long)m->P * (bott / 8) * pl.readsPad;
-  pl.off_t = take((size_t)m->L * pl.t_layer_pieces * 16);
-  pl.off_pool = take((size_t)pl.S * m->P * kC * 4);
+  for (int i = 0; i < 2; ++i) pl.off_t[i] = take((size_t)m->L * pl.t_layer_pieces * 16);       // two sets: passes k and k+1 are in flight together
+  for (int i = 0; i < 2; ++i) pl.off_pool[i] = take((size_t)pl.S * m->P * kC * 4);
   pl.off_agree = take((size_t)pl.S * 2 * m->R);
   pl.hw_layer_stride = pl.readsPad * bott;
-  pl.off_hw = take((size_t)m->L * pl.hw_layer_stride * 4);
+  for (int i = 0; i < 2; ++i) pl.off_hw[i] = take((size_t)m->L * pl.hw_layer_stride * 4);
   pl.off_fcin = take((size_t)pl.fcKC * pl.BcPad * 16);           // [BcPad][fcInPad] bf16, row-major
   pl.maxN = DAN_HEAD_PAD;
   for (int i = 0; i < m->cfg.num_fc; ++i) {
@@ -723,6 +755,11 @@ void dan_bf16_free(dan_model* m) {
   for (int i = 0; i < DAN_MAX_FC; ++i) cudaFree(bw->fcw[i]);
   cudaFree(bw->headw);
   cudaFree(bw->comp_bias_ptrs);
+  if (bw->side) {
+    cudaStreamDestroy(bw->side);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(bw->ev_seg1[i]); cudaEventDestroy(bw->ev_pm[i]); cudaEventDestroy(bw->ev_seg2[i]); cudaEventDestroy(bw->ev_pf[i]); cudaEventDestroy(bw->ev_comp[i]); cudaEventDestroy(bw->ev_hw[i]); }
+    cudaEventDestroy(bw->ev_side);
+  }
   delete bw;
   m->bf16_store = nullptr;
 }
@@ -736,17 +773,21 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
   const RowGeom g = m->geom;
   const int L = m->L, bott = m->bott, P = m->P, R = m->R;
   uint4* X0 = reinterpret_cast<uint4*>(base + pl.off_x0);
-  uint4* H[3]; for (int i = 0; i < 3; ++i) H[i] = reinterpret_cast<uint4*>(base + pl.off_h[i]);
-  uint4* T = reinterpret_cast<uint4*>(base + pl.off_t);
-  float* POOL = reinterpret_cast<float*>(base + pl.off_pool);
+  uint4* H[4]; for (int i = 0; i < 4; ++i) H[i] = reinterpret_cast<uint4*>(base + pl.off_h[i]);
+  uint4* Tset[2] = {reinterpret_cast<uint4*>(base + pl.off_t[0]), reinterpret_cast<uint4*>(base + pl.off_t[1])};
+  float* POOLset[2] = {reinterpret_cast<float*>(base + pl.off_pool[0]), reinterpret_cast<float*>(base + pl.off_pool[1])};
+  uint4* T = Tset[0];
+  float* POOL = POOLset[0];
   uint8_t* AGREE = reinterpret_cast<uint8_t*>(base + pl.off_agree);
   const bool fast_encode = m->cfg.embed_dim == 20 && m->cfg.use_q_scores && m->cfg.use_strands && m->cfg.use_reads_ref_var_mask && m->CinPad == 48 && P <= 512 &&
                            encode_prod_smem_bytes(R) <= 48 * 1024;
-  float* HW = reinterpret_cast<float*>(base + pl.off_hw);
+  float* HWset[2] = {reinterpret_cast<float*>(base + pl.off_hw[0]), reinterpret_cast<float*>(base + pl.off_hw[1])};
+  float* HW = HWset[0];
   uint4* FCIN = reinterpret_cast<uint4*>(base + pl.off_fcin);
   // highway compression (model.py:776) of every layer of a pass as ONE batched GEMM: HW[l][read][o] = T[l][read][:] . Wc[l][o][:]
-  auto run_compression = [&](int l0, int nl, int reads) -> int {
+  auto run_compression = [&](int l0, int nl, int reads, int set = 0) -> int {
     const long K = (long)P * bott;
+    uint4* T = Tset[set]; float* HW = HWset[set];
     Gemm2Operand A{T + (long)l0 * pl.t_layer_pieces, reads, K * 2, pl.t_layer_pieces * 16};
     Gemm2Operand B{bw->wcomp[l0], bott, K * 2, K * 2 * bott};
     Gemm2Params gp{};
@@ -778,48 +819,17 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
   // The fused path loads and stores exactly the P data rows of every read and keeps its zero rows in shared memory.
   if (!fused) DAN_CUDA_TRY(cudaMemsetAsync(base + pl.off_zero_begin, 0, pl.off_zero_end - pl.off_zero_begin, st));
 
-  EncodeParams ep{};
-  ep.in = in; ep.emb = m->emb; ep.pe = m->pe; ep.D = m->cfg.embed_dim; ep.Cin = m->Cin; ep.CinPad = m->CinPad;
-  ep.use_q = m->cfg.use_q_scores; ep.use_s = m->cfg.use_strands; ep.use_m = m->cfg.use_reads_ref_var_mask; ep.g = g;
-
-  for (int c0 = 0; c0 < batch; c0 += pl.Bc) {
-    const int nb = batch - c0 < pl.Bc ? batch - c0 : pl.Bc;
-    if (m->fcInPad != m->fcIn) DAN_CUDA_TRY(cudaMemsetAsync(FCIN, 0, (size_t)pl.fcKC * pl.BcPad * 16, st));
-    for (int s0 = 0; s0 < nb; s0 += pl.S) {
-      const int ns = nb - s0 < pl.S ? nb - s0 : pl.S;
-      const long rows = g.rows_of(ns);
-      const int num_tiles = (int)((rows + 127) / 128);
-      if (fast_encode) {
-        DanProfScope ps(DAN_PROF_ENCODE, st);
-        agree_bits_kernel<<<ns, 128, 0, st>>>(in, (long)c0 + s0, P, R, AGREE);
-        encode_prod_bf16_kernel<<<dim3((P + kEncPB - 1) / kEncPB, ns), 256, encode_prod_smem_bytes(R), st>>>(in, m->emb, m->pe, AGREE, (long)c0 + s0, g, X0, pl.kstride);
-        dan_count_launch(2);
-      } else {
-        DanProfScope ps(DAN_PROF_ENCODE, st);
-        encode_rows_bf16_kernel<<<ns, 256, enc_smem, st>>>(ep, (long)c0 + s0, X0, pl.kstride);
-        dan_count_launch();
-      }
-      DAN_CUDA_TRY(cudaGetLastError());
-      const uint4* cur = X0;
-      int hsel = 0;
-      if (fused) {
-        // ---- fused path: one persistent launch per segment of layers without a pool-add in between (dan_stack.cuh) ----
-        int l = 0;
-        while (l < L) {
-          int l_end = l + 1;
-          while (l_end < L && !m->cfg.pool_after[l_end - 1] && l_end - l < kStkMaxSeg) ++l_end;
-          const uint4* seg_in = cur;
-          const bool with_pool = l > 0 && m->cfg.pool_after[l - 1];      // the pool-add is fused into the segment's load
-          uint4* next = H[(hsel + 1) % 3];
+  // one persistent launch of dan_stack_kernel over layers [l, l_end) of a pass (dan_stack.cuh)
+  auto launch_segment = [&](int l, int l_end, const uint4* seg_in, uint4* next, int set, bool with_pool, int ns) -> int {
           StackParams sp{};
           sp.in = seg_in; sp.in_kstride = pl.kstride; sp.out = next; sp.out_kstride = pl.kstride;
           sp.t_reads_stride = pl.readsPad; sp.num_reads = ns * R; sp.P = P; sp.pitch = g.pitch; sp.bott = bott > 0 ? bott : 32;
           sp.num_layers = l_end - l;
-          sp.pool = with_pool ? POOL : nullptr; sp.reads_per_cand = R;
+          sp.pool = with_pool ? POOLset[set] : nullptr; sp.reads_per_cand = R;
           for (int k = l; k < l_end; ++k) {
             StackLayer& SL = sp.layer[k - l];
             SL.wstream = bw->wstream[k]; SL.wreplica_stride = bw->wstream_bytes[k]; SL.chan = bw->chan_dev + (size_t)k * 4 * kC; SL.bbias = m->bottB[k];
-            SL.tout = T + (long)k * pl.t_layer_pieces;
+            SL.tout = Tset[set] + (long)k * pl.t_layer_pieces;
             SL.kc_in = (k == 0 ? m->CinPad : kC) / 8; SL.conv_blocks = 3 * SL.kc_in / 2;
             SL.dil = m->cfg.dilation[k]; SL.residual = m->cfg.is_residual[k]; SL.highway = m->cfg.highway;
           }
@@ -859,6 +869,119 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
             fprintf(stderr, "[stackprof] layers %d-%d reads %d grid %d: issuer0 total %.0f dep-wait %.0f | epi0 wait %.0f main %.0f bott %.0f | epi1 wait %.0f main %.0f bott %.0f | store+load wait %.0f %.0f | issuer1 total %.0f dep-wait %.0f | weight-wait %.0f %.0f (cycles, mean over CTAs)\n",
                     l + 1, l_end, sp.num_reads, grid, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], a[11], a[12], a[13]);
           }
+          return DAN_OK;
+  };
+
+  EncodeParams ep{};
+  ep.in = in; ep.emb = m->emb; ep.pe = m->pe; ep.D = m->cfg.embed_dim; ep.Cin = m->Cin; ep.CinPad = m->CinPad;
+  ep.use_q = m->cfg.use_q_scores; ep.use_s = m->cfg.use_strands; ep.use_m = m->cfg.use_reads_ref_var_mask; ep.g = g;
+
+  auto encode_pass = [&](long cand0, int ns) -> int {
+    if (fast_encode) {
+      DanProfScope ps(DAN_PROF_ENCODE, st);
+      agree_bits_kernel<<<ns, 128, 0, st>>>(in, cand0, P, R, AGREE);
+      encode_prod_bf16_kernel<<<dim3((P + kEncPB - 1) / kEncPB, ns), 256, encode_prod_smem_bytes(R), st>>>(in, m->emb, m->pe, AGREE, cand0, g, X0, pl.kstride);
+      dan_count_launch(2);
+    } else {
+      DanProfScope ps(DAN_PROF_ENCODE, st);
+      encode_rows_bf16_kernel<<<ns, 256, enc_smem, st>>>(ep, cand0, X0, pl.kstride);
+      dan_count_launch();
+    }
+    DAN_CUDA_TRY(cudaGetLastError());
+    return DAN_OK;
+  };
+
+  // ---- software pipeline over the passes of one FC chunk (PROD structure: segment A = layers before the read-mean pool-add,
+  // segment B = the rest). The HBM-bound read-axis reductions run on a side stream NEXT TO the persistent stack kernel of the
+  // following pass (64-thread CTAs without shared memory fit beside its 640 threads / 226 KB on every SM):
+  //   main : enc(0) A(0) | enc(1) A(1) B(0) comp(0) | enc(2) A(2) B(1) comp(1) | ...
+  //   side :      mean(0)      mean(1)  final(0) hw(0)      mean(2)  final(1) hw(1)
+  // Two sets of H / T / POOL / HW buffers (pass parity); events order producer -> consumer and consumer -> buffer reuse.
+  int l_split = 0;
+  for (int l = 1; l < L; ++l) if (m->cfg.pool_after[l - 1]) { if (!l_split) l_split = l; else { l_split = -1; break; } }
+  // EXPERIMENTAL, opt-in (DAN_B200_PIPE=1): correct (GPU tests pass with it), but measured no gain — the side-stream kernels do not
+  // become resident next to the persistent stack kernel on this driver (their class time stretches to the stack kernel's), so the
+  // schedule degenerates to the sequential one. Kept for round 2.
+  static const bool want_pipe = getenv("DAN_B200_PIPE") != nullptr;
+  const bool pipelined = fused && l_split > 0 && l_split <= kStkMaxSeg && L - l_split <= kStkMaxSeg && m->cfg.highway && want_pipe &&
+                         !getenv("DAN_B200_STACKPROF") && !getenv("DAN_B200_STACKTRACE") && !getenv("DAN_B200_SYNC");
+  if (pipelined && !bw->side) {
+    // same L1 / shared-memory split as the stack kernel, or the SM cannot hold both kernels' CTAs at once
+    DAN_CUDA_TRY(cudaFuncSetAttribute(pool_mean_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DAN_CUDA_TRY(cudaFuncSetAttribute(pool_final_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DAN_CUDA_TRY(cudaFuncSetAttribute(highway_finish_bf16_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    DAN_CUDA_TRY(cudaStreamCreateWithFlags(&bw->side, cudaStreamNonBlocking));
+    cudaEvent_t* evs[] = {bw->ev_seg1, bw->ev_pm, bw->ev_seg2, bw->ev_pf, bw->ev_comp, bw->ev_hw};
+    for (auto e : evs) for (int i = 0; i < 2; ++i) DAN_CUDA_TRY(cudaEventCreateWithFlags(&e[i], cudaEventDisableTiming));
+    DAN_CUDA_TRY(cudaEventCreateWithFlags(&bw->ev_side, cudaEventDisableTiming));
+  }
+  auto run_chunk_pipelined = [&](int c0, int nb) -> int {
+    cudaStream_t ss = bw->side;
+    const int np = (nb + pl.S - 1) / pl.S;
+    auto pass_ns = [&](int k) { const int s0 = k * pl.S; return nb - s0 < pl.S ? nb - s0 : pl.S; };
+    auto seg_a = [&](int k) -> int {
+      const int b = k & 1, ns = pass_ns(k);
+      int rc2;
+      if ((rc2 = encode_pass((long)c0 + (long)k * pl.S, ns))) return rc2;
+      if ((rc2 = launch_segment(0, l_split, X0, H[b], b, false, ns))) return rc2;
+      DAN_CUDA_TRY(cudaEventRecord(bw->ev_seg1[b], st));
+      DAN_CUDA_TRY(cudaStreamWaitEvent(ss, bw->ev_seg1[b], 0));
+      { DanProfScope ps(DAN_PROF_POOL, ss); pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, ss>>>(H[b], pl.kstride, POOLset[b], g); }
+      dan_count_launch();
+      DAN_CUDA_TRY(cudaEventRecord(bw->ev_pm[b], ss));
+      return DAN_OK;
+    };
+    int rc2;
+    if ((rc2 = seg_a(0))) return rc2;
+    for (int k = 0; k < np; ++k) {
+      const int b = k & 1, ns = pass_ns(k), s0 = k * pl.S;
+      if (k + 1 < np && (rc2 = seg_a(k + 1))) return rc2;
+      DAN_CUDA_TRY(cudaStreamWaitEvent(st, bw->ev_pm[b], 0));
+      if (k >= 2) DAN_CUDA_TRY(cudaStreamWaitEvent(st, bw->ev_pf[b], 0));                 // H[2 + b] has been reduced by pass k-2's pool kernel
+      if ((rc2 = launch_segment(l_split, L, H[b], H[2 + b], b, true, ns))) return rc2;
+      DAN_CUDA_TRY(cudaEventRecord(bw->ev_seg2[b], st));
+      DAN_CUDA_TRY(cudaStreamWaitEvent(ss, bw->ev_seg2[b], 0));
+      { DanProfScope ps(DAN_PROF_POOL, ss); pool_final_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, ss>>>(H[2 + b], pl.kstride, FCIN, pl.fcKC, s0, g, m->cfg.skip_final_maxpool); }
+      dan_count_launch();
+      DAN_CUDA_TRY(cudaEventRecord(bw->ev_pf[b], ss));
+      if (k >= 2) DAN_CUDA_TRY(cudaStreamWaitEvent(st, bw->ev_hw[b], 0));                 // HW set b has been consumed by pass k-2
+      if ((rc2 = run_compression(0, L, ns * R, b))) return rc2;
+      DAN_CUDA_TRY(cudaEventRecord(bw->ev_comp[b], st));
+      DAN_CUDA_TRY(cudaStreamWaitEvent(ss, bw->ev_comp[b], 0));
+      const int Lh = m->cfg.concat_hw_reads ? L : 1;
+      { DanProfScope ps(DAN_PROF_POOL, ss); highway_finish_bf16_kernel<<<grid_for((long)ns * Lh * R * (bott / 8)), 256, 0, ss>>>(
+          HWset[b], pl.hw_layer_stride, bw->comp_bias_ptrs, L, bott, R, m->cfg.concat_hw_reads, FCIN, pl.fcKC, m->pooled / 8, s0, ns); }
+      dan_count_launch();
+      DAN_CUDA_TRY(cudaEventRecord(bw->ev_hw[b], ss));
+    }
+    DAN_CUDA_TRY(cudaGetLastError());
+    DAN_CUDA_TRY(cudaEventRecord(bw->ev_side, ss));
+    DAN_CUDA_TRY(cudaStreamWaitEvent(st, bw->ev_side, 0));                               // FC reads every row of FCIN
+    return DAN_OK;
+  };
+
+  for (int c0 = 0; c0 < batch; c0 += pl.Bc) {
+    const int nb = batch - c0 < pl.Bc ? batch - c0 : pl.Bc;
+    if (m->fcInPad != m->fcIn) DAN_CUDA_TRY(cudaMemsetAsync(FCIN, 0, (size_t)pl.fcKC * pl.BcPad * 16, st));
+    if (pipelined) {
+      if ((rc = run_chunk_pipelined(c0, nb))) return rc;
+    } else
+    for (int s0 = 0; s0 < nb; s0 += pl.S) {
+      const int ns = nb - s0 < pl.S ? nb - s0 : pl.S;
+      const long rows = g.rows_of(ns);
+      const int num_tiles = (int)((rows + 127) / 128);
+      if ((rc = encode_pass((long)c0 + s0, ns))) return rc;
+      const uint4* cur = X0;
+      int hsel = 0;
+      if (fused) {
+        // ---- fused path: one persistent launch per segment of layers without a pool-add in between (dan_stack.cuh) ----
+        int l = 0;
+        while (l < L) {
+          int l_end = l + 1;
+          while (l_end < L && !m->cfg.pool_after[l_end - 1] && l_end - l < kStkMaxSeg) ++l_end;
+          const bool with_pool = l > 0 && m->cfg.pool_after[l - 1];      // the pool-add is fused into the segment's load
+          uint4* next = H[(hsel + 1) % 3];
+          if ((rc = launch_segment(l, l_end, cur, next, 0, with_pool, ns))) return rc;
           if (m->cfg.pool_after[l_end - 1] && l_end < L) {
             { DanProfScope ps(DAN_PROF_POOL, st); pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(next, pl.kstride, POOL, g); }
             dan_count_launch();

@@ -230,7 +230,13 @@ __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // ---- named barrier for a subset of the CTA's warps ---------------------------------------------------------
-__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+// The barrier id is an immediate: with a register id ptxas has to reserve all 16 hardware barriers for the CTA, and no other CTA
+// (e.g. a small kernel of another stream) can then be resident on the SM next to it.
+template <uint32_t kId>
+__device__ __forceinline__ void named_bar_sync_imm(uint32_t threads) { asm volatile("bar.sync %0, %1;" ::"n"(kId), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t threads) {      // id 1 or 2
+  if (id == 1) named_bar_sync_imm<1>(threads); else named_bar_sync_imm<2>(threads);
+}
 
 // ---- misc -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
