@@ -303,12 +303,21 @@ def run_b200(args):
         "whole_forward_frac": (value / world * flops_total / 1e12 / peak) if peak else None,
         "hbm_frac_algorithmic": value / world * 60923 / (peaks["hbm_gbs"] * 1e9),
     }
+    if args.precision == "fp32":
+        # the 1e-4-parity path runs on the CUDA-core FMA pipe and has no per-class event hooks: whole-forward FLOP
+        # rate against the fp32 FMA peak of the part (148 SMs x 128 lanes x 2 FLOP x max SM clock)
+        fma_peak = 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
+        ach = value / world * flops_total / 1e12
+        roofline = {"bound": "fp32_fma (CUDA cores)", "kernel": "whole forward (sgemm_taps_kernel dominates)", "achieved": ach, "peak": fma_peak,
+                    "unit": "TFLOP/s", "frac": ach / fma_peak, "traffic": None, "peak_source": "nominal: 148 SMs x 128 FMA lanes x 2 x sm_max_mhz"}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD, "candidates_per_step_per_gpu": B, "model": "PROD", "reads": R, "window": P,
-                   "precision": args.precision, "l2_policy": f"inputs per step {in_bytes/1e6:.0f} MB > 126 MB L2, no flush",
+                   "precision": args.precision,
+                   "l2_policy": (f"inputs per step {in_bytes/1e6:.0f} MB > 126 MB L2, no flush" if in_bytes > 126e6 else
+                                 f"inputs per step {in_bytes/1e6:.0f} MB; intermediates of a step ({B * 31.3:.0f} MB written and re-read) exceed the 126 MB L2, no flush"),
                    "parallelism": f"candidate-sharded x{world}, no collective"},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": in_bytes, "d2h_bytes_per_step": B * _lib.NUM_HEAD_OUTPUTS * 4,
                 "ms_per_step": ms_e2e / args.steps},
