@@ -844,7 +844,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           { DanProfScope ps(DAN_PROF_CONV_STACK, st);
             if (sp.trace) dan_stack_kernel<3><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);                  // development builds of the kernel
             else if (sp.prof) dan_stack_kernel<2><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);
-            else if (sp.debug & ~64) dan_stack_kernel<1><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);
+            else if (sp.debug) dan_stack_kernel<1><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp);
             else dan_stack_kernel<0><<<grid, kStkThreads, kStkSmemBytes, st>>>(sp); }
           dan_count_launch();
           DAN_CUDA_TRY(cudaGetLastError());

@@ -37,8 +37,6 @@ constexpr int kStkBuf = kKC * kStkPlane;       // bytes per read buffer (54272)
 constexpr int kStkStageBytes = 8192;   // weight-ring stage = two k-step blocks of 4 KB
 constexpr int kStkStages = 14;         // stages of the weight ring shared by the two slots (>= largest op (12) + prefetch)
 constexpr int kStkMaxSeg = 8;          // layers per segment
-constexpr uint32_t kStkSlotCols = 256, kStkBottCol0 = 224, kStkBottCol1 = 480;   // TMEM columns: slot s accumulator at 256 s (208 wide); shared
-                                                                                 // bottleneck accumulator: position tile 0 at 224, tile 1 at 480 (32 columns each, 32-aligned)
 constexpr int kStkRegsIssue = 56, kStkRegsEpi = 104;   // setmaxnreg redistributes the launch allocation (640 x 96): 128 x 56 + 512 x 104 = 60416 <= 61440
 constexpr int kStkSmemHeader = 3072;   // barriers, TMEM pointer, bottleneck biases of the segment
 constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + kStkStages * kStkStageBytes;
@@ -69,7 +67,6 @@ struct StackParams {
 struct StackSmem {
   uint64_t w_full[kStkStages], w_empty[kStkStages];
   uint64_t acc_full[2], act_ready[2], in_full[2];
-  uint64_t bott_full[2], bott_free;    // deferred bottleneck epilogue: per-slot "accumulator written", shared "accumulator drained"
   uint32_t tmem_base;
   uint32_t issued_ops;                 // ops fully issued by slot 0's issuer (slot 1 runs one op behind, see the issuer)
   float bbias[kStkMaxSeg][64];
@@ -94,11 +91,6 @@ __device__ __forceinline__ void stk_trace(const StackParams& p, int role, int& n
 // kDev: 0 = production, 1 = honours the debug skip flags only, 2 = + cycle counters, 3 = + event trace instead (development builds)
 template <int kDev>
 __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_constant__ StackParams p) {
-  // Deferred bottleneck epilogue (32 bottleneck channels): the bottleneck MMAs of layer l go to their own TMEM accumulator and the
-  // next layer's conv is issued right behind them; the bottleneck epilogue (TMEM -> relu -> T in global memory) then runs UNDER that
-  // conv instead of in front of it. The two slots share the accumulator and take turns (slot 0, slot 1, slot 0, ...).
-  // EXPERIMENTAL, off by default (development opt-in: DAN_B200_STACKDEBUG=64): correct on small inputs but deadlocks on long runs.
-  const bool defer = p.bott == 32 && (p.debug & 64);
   const bool prof_on = kDev == 2 && p.prof != nullptr, trace_on = kDev == 3 && p.trace != nullptr;
   extern __shared__ __align__(1024) uint8_t smem[];
   StackSmem* sm = reinterpret_cast<StackSmem*>(smem);
@@ -119,10 +111,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
   if (threadIdx.x == 0) {
     for (int i = 0; i < kStkStages; ++i) { mbar_init(&sm->w_full[i], 1); mbar_init(&sm->w_empty[i], 2); }   // both slots release a stage
     sm->issued_ops = 0;
-    mbar_init(&sm->bott_free, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], kStkEpiThreads); mbar_init(&sm->in_full[s], 1);
-      mbar_init(&sm->bott_full[s], 1);
     }
     fence_mbar_init();
   }
@@ -205,9 +195,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     volatile uint32_t* const issued = &sm->issued_ops;
     uint32_t gops = 0;                                                                            // ops started by this issuer
     int tr_n = 0;
-    const uint32_t d_main = tmem_base + (uint32_t)s * kStkSlotCols;
-    const uint32_t d_bott0 = defer ? tmem_base + kStkBottCol0 : d_main, d_bott1 = defer ? tmem_base + kStkBottCol1 : d_main + (uint32_t)p.bott;
-    uint32_t arc = 0, kb = 0;                         // act_ready phases consumed, bottleneck ops issued
+    const uint32_t d_main = tmem_base + (uint32_t)s * 256u;
     const uint32_t x_lo = (smem_u32(bufs) >> 4) + (uint32_t)s * (kStkBuf >> 4) + kStkLead;       // centre row of chunk plane 0
     constexpr uint32_t kStep = 2 * (kStkPlane >> 4);                                              // one k-step = two chunk planes
     uint32_t wi = 0, wp = 0, opc = 0;
@@ -228,22 +216,22 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       tc_fence_after();
     };
     auto adv2 = [&](uint32_t wi1, uint32_t wp1) { wi = wi1 + 1; wp = wp1; if (wi == kStkStages) { wi = 0; wp ^= 1; } };
-    auto wait_dep = [&](bool first_of_read, int k, bool wait_ready = true) {
+    auto wait_dep = [&](bool first_of_read, int k) {
       long long c0 = 0; if (prof_on) c0 = clock64();
       // slot 1 starts op n only after slot 0 has issued all of its op n: the tensor pipe then runs slot 1's MMAs under slot 0's
       // epilogue (and vice versa) instead of both slots computing and then both draining, and the lag between the two
       // consumers of the shared weight ring stays within one op (<= 12 of the 14 stages).
       if (s == 1 && !(p.debug & 8)) { uint32_t spins = 0; while (*issued <= gops) { if (++spins > (1u << 28)) __trap(); } }
       ++gops;
-      if (wait_ready) { mbar_wait(&sm->act_ready[s], arc & 1); ++arc; }
+      mbar_wait(&sm->act_ready[s], opc & 1);
       if (first_of_read) mbar_wait(&sm->in_full[s], (uint32_t)k & 1);
       tc_fence_after();
       if (prof_on) t_dep += clock64() - c0;
       if (trace_on && lane == 0) stk_trace(p, s, tr_n, (uint32_t)s << 28 | 1u << 24 | (gops & 0xFFFFu));
     };
-    auto op_done = [&](uint64_t* full_bar) {
+    auto op_done = [&]() {
       if (elect_one()) {
-        umma_commit(full_bar);
+        umma_commit(&sm->acc_full[s]);
         if (s == 0) { __threadfence_block(); *issued = gops; }
       }
       __syncwarp();
@@ -267,12 +255,6 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             __syncwarp();
             if (++wi == kStkStages) { wi = 0; wp ^= 1; }
           }
-          if (defer && L.highway) {        // pass the shared bottleneck accumulator's turn on
-            mbar_wait(&sm->bott_free, ((2 * kb + (uint32_t)s) & 1) ^ 1);
-            if (elect_one()) mbar_arrive(&sm->bott_free);
-            __syncwarp();
-            ++kb;
-          }
         }
         break;
       }
@@ -281,7 +263,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         const int residual = L.residual, highway = L.highway, ksteps = L.kc_in / 2, total = L.conv_blocks;
         const uint32_t dil = (uint32_t)L.dil;
         // ---- conv: D[cout][pos] = sum over taps and input-channel k-steps ----
-        wait_dep(l == 0, k, l == 0 || !(defer && p.layer[l - 1].highway));   // behind a deferred bottleneck: same activations, no new wait
+        wait_dep(l == 0, k);
         if ((ksteps & 3) == 0) {
           // two ring stages (4 k-steps) per iteration: both full-barrier probes are in flight together and the four MMAs and
           // the two stage releases go out from one elected region — a single warp retires a dependent instruction only every
@@ -326,7 +308,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             stage_done();
           }
         }
-        op_done(&sm->acc_full[s]);
+        op_done();
         // ---- residual 1x1: accumulates on x + b_res stored by the epilogue ----
         if (residual) {
           wait_dep(false, 0);
@@ -348,12 +330,11 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             bd_lo += 4 * kStep;
             adv2(wi1, wp1);
           }
-          op_done(&sm->acc_full[s]);
+          op_done();
         }
         // ---- bottleneck 1x1, positions-as-M orientation: A = activation rows (two 128-row tiles), B = weights ----
         if (highway) {
           wait_dep(false, 0);
-          if (defer) mbar_wait(&sm->bott_free, ((2 * kb + (uint32_t)s) & 1) ^ 1);      // the other slot's previous turn has been drained
           uint32_t xa_lo = x_lo | b_lbo_x;
           for (int blk = 0; blk < kKC / 2; blk += bott_per_stage) {
             wait_w();
@@ -362,8 +343,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
               uint32_t xa = xa_lo, wl = w_lo;
               for (int u = 0; u < bott_per_stage; ++u) {
                 if (do_mma) {
-                  umma_bf16(d_bott0, stk_desc(xa, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
-                  umma_bf16(d_bott1, stk_desc(xa + 128u, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
+                  umma_bf16(d_main, stk_desc(xa, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
+                  umma_bf16(d_main + (uint32_t)p.bott, stk_desc(xa + 128u, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
                 }
                 xa += kStep;
                 wl += (uint32_t)p.bott * 2u;
@@ -374,8 +355,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             xa_lo += (uint32_t)bott_per_stage * kStep;
             if (++wi == kStkStages) { wi = 0; wp ^= 1; }
           }
-          op_done(defer ? &sm->bott_full[s] : &sm->acc_full[s]);
-          ++kb;
+          op_done();
         }
       }
     }
@@ -389,10 +369,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     // thread 0 of the slot's group also moves the slot's reads in and out ==========================================
     const int s = warp >> 3, h = (warp >> 2) & 1, q = warp & 3;
     const int gtid = threadIdx.x & (kStkEpiThreads - 1);
-    const uint32_t tbase = tmem_base + (uint32_t)s * kStkSlotCols + ((uint32_t)(32 * q) << 16);
-    // bottleneck accumulator of this warp's position tile h
-    const uint32_t tbott = (defer ? tmem_base + (h ? kStkBottCol1 : kStkBottCol0) : tmem_base + (uint32_t)s * kStkSlotCols + (uint32_t)(h * p.bott)) + ((uint32_t)(32 * q) << 16);
-    uint32_t kbe = 0;                                  // bottleneck epilogues done by this slot
+    const uint32_t tbase = tmem_base + (uint32_t)s * 256u + ((uint32_t)(32 * q) << 16);
     const uint32_t buf_addr = smem_u32(bufs + (size_t)s * kStkBuf);
     // stmatrix / ldmatrix row address of this thread for position group 0: matrix lane>>3 = chunk plane 4q + (lane>>3), row lane&7
     const uint32_t saddr0 = buf_addr + (uint32_t)(4 * q + (lane >> 3)) * kStkPlane + (uint32_t)(kStkLead + (lane & 7)) * 16;
@@ -476,9 +453,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           }
         }
         if (L.highway) {
-          if (defer) mbar_wait(&sm->bott_full[s], kbe & 1);
-          else { mbar_wait(&sm->acc_full[s], opc & 1); ++opc; }
-          ++kbe;
+          mbar_wait(&sm->acc_full[s], opc & 1);
           tc_fence_after();
           if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
           if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 3u << 24 | (eops & 0xFFFFu));
@@ -487,7 +462,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           const int pos = 128 * h + 32 * q + lane;
           for (int cc = 0; do_epi && cc < p.bott / 32; ++cc) {
             uint32_t r[32];
-            tmem_ld32(tbott + (uint32_t)(cc * 32), r);
+            tmem_ld32(tbase + (uint32_t)(h * p.bott + cc * 32), r);
             tmem_ld_wait();
             if (pos < p.P) {
               const float* bb = &sm->bbias[l][cc * 32];
@@ -503,12 +478,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             }
           }
           tc_fence_before();
-          if (defer) {                                    // hand the shared accumulator to the other slot; nothing waits for this epilogue
-            named_bar_sync(1 + s, kStkEpiThreads);
-            if (gtid == 0) mbar_arrive(&sm->bott_free);
-          } else if (!last) {
-            mbar_arrive(&sm->act_ready[s]);
-          }
+          if (!last) mbar_arrive(&sm->act_ready[s]);
+          ++opc;
           if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
           if (prof) { const long long t1 = clock64(); t_bott += t1 - t0; t0 = t1; }
         }
