@@ -133,7 +133,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     mbar_expect_tx(&sm->in_full[s], plane_bytes_in * in_kc);
     const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
     uint8_t* dst = bufs + (size_t)s * kStkBuf + kStkLead * 16;
-    for (int kc = 0; kc < in_kc; ++kc) bulk_g2s(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s]);
+    const uint64_t once = l2_policy_evict_first();          // activations stream through: read once, written once
+    for (int kc = 0; kc < in_kc; ++kc) bulk_g2s_hint(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s], once);
     if (i + 2 < n_reads) {       // the slot's next read: pull it into L2 now so that its load (on the slot's critical path) is an L2 hit
       const uint4* nxt = src + 2 * (long)p.pitch;
       for (int kc = 0; kc < in_kc; ++kc) bulk_prefetch_l2(nxt + kc * p.in_kstride, plane_bytes_in);
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     // stage (empty-barrier probe + expect_tx + copy issue), which is close to the rate at which the tensor pipe drains a stage.
     if (lane == 0 && !(kDev != 0 && (p.debug & 16))) {
       const uint32_t mine = (uint32_t)(warp - 16);
+      const uint64_t keep = l2_policy_evict_last();          // the weight images are re-read by every CTA for every pair of reads
       uint32_t idx = 0, par = 1, seq = 0;     // first pass over the ring: the "empty" phase counts as complete
       auto emit = [&](const uint8_t* src, uint32_t bytes) {
         for (uint32_t off = 0; off < bytes; off += kStkStageBytes) {
@@ -160,7 +162,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             const uint32_t n = min((uint32_t)kStkStageBytes, bytes - off);
             mbar_wait(&sm->w_empty[idx], par);
             mbar_expect_tx(&sm->w_full[idx], n);
-            bulk_g2s(rings + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[idx]);
+            bulk_g2s_hint(rings + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[idx], keep);
           }
           if (++idx == kStkStages) { idx = 0; par ^= 1; }
         }
@@ -448,7 +450,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           if (gtid == 0) {
             uint4* dst = p.out + kLead + (long)(r_begin + i) * p.pitch;
             const uint8_t* src = bufs + (size_t)s * kStkBuf + kStkLead * 16;
-            for (int kc = 0; kc < kKC; ++kc) bulk_s2g(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in);
+            const uint64_t once = l2_policy_evict_first();
+            for (int kc = 0; kc < kKC; ++kc) bulk_s2g_hint(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in, once);
             bulk_commit();
           }
         }
