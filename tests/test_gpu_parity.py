@@ -227,3 +227,44 @@ def test_feeder_end_to_end_matches_direct_forward():
     assert rel_err(got, want) < 1e-3           # same kernels; split-K atomics order may differ between batch shapes
     b, v = scores_from_heads(torch.from_numpy(got))
     assert format_vcf_info(b.numpy(), v.numpy())[0].startswith("BP=")
+
+
+def test_bf16_layerwise_fallback_agrees_with_fused_path(monkeypatch):
+    """Configurations the fused stack kernel does not take (window != 201, a residual layer right behind a pool-add) run layer by
+    layer (dan_layer_kernel); the same inputs through both code paths must give the same numbers up to bf16 re-rounding."""
+    g = load_golden("prod_smallfc_mixed")
+    cfg = g["cfg"]
+    model = build_model(cfg, synth_state_dict(cfg, seed=g["seed"]), precision="bf16")
+    fused = _heads(model, g["arrays"])
+    monkeypatch.setenv("DAN_B200_LAYERWISE", "1")
+    layerwise = _heads(model, g["arrays"])
+    assert rel_err(layerwise, g["heads"]) < BF16_TOL
+    assert rel_err(layerwise, fused) < BF16_TOL
+
+
+def test_capi_rejects_bad_calls():
+    """Error behaviour of the C-ABI: status codes + dan_last_error text, never a crash."""
+    import ctypes as C
+    from dl4vc_b200 import _lib
+    lib = _lib.load_library()
+    cfg = small_config()
+    model = build_model(cfg, synth_state_dict(cfg, seed=9), precision="bf16")
+    batch = make_pileups(2, seed=1)
+    with pytest.raises(RuntimeError, match="reads must be"):
+        model.forward_heads(torch.zeros((2, 100, 201), dtype=torch.uint8), torch.from_numpy(batch.ref))
+    h = model._state(model._device()).handle
+    # workspace too small
+    r = torch.from_numpy(batch.reads).cuda(); z = torch.from_numpy(batch.ref).cuda()
+    out = torch.empty((2, 27), device="cuda"); ws = torch.empty(1024, dtype=torch.uint8, device="cuda")
+    rc = lib.dan_forward(h, _lib.PRECISION_BF16, r.data_ptr(), r.data_ptr(), r.data_ptr(), z.data_ptr(), z.data_ptr(), z.data_ptr(), 2,
+                         out.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == -4 and b"workspace" in lib.dan_last_error()
+    # null inputs / negative batch
+    rc = lib.dan_forward(h, _lib.PRECISION_BF16, None, None, None, None, None, None, 2, out.data_ptr(), ws.data_ptr(), ws.numel(), None)
+    assert rc == -1
+    assert lib.dan_model_set_pass_candidates(h, 0) == -1
+    # unsupported shape at creation
+    bad = _lib.DanConfigC()
+    bad.total_conv_layers = 99
+    hh = C.c_void_p()
+    assert lib.dan_model_create(C.byref(bad), C.byref(hh)) == -2 and not hh.value
