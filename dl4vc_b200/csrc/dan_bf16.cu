@@ -27,10 +27,10 @@ using namespace ptx;
 constexpr int kC = 128;               // channels (bf16 path is specialised for the shipped width)
 constexpr int kKC = kC / 8;           // 16-byte pieces per row
 constexpr int kLead = 8;
-// Every CTA of the fused kernel streams the same few hundred KB of layer weights at about the same time; with a single
-// copy those reads pile up on the handful of L2 slices that own the current lines (measured: 8 KB per ~950 cycles per
-// SM). CTA c therefore reads replica c % kWeightReplicas.
-constexpr int kWeightReplicas = 16;              // zero rows in front of every row matrix (>= largest dilation)
+// Every CTA of the fused kernel streams the same few hundred KB of layer weights at about the same time; CTA c reads replica
+// c % kWeightReplicas so that the reads spread over more L2 slices. (With per-slot rings 16 copies helped; with the shared ring,
+// the evict-last L2 policy and two producer threads 1-4 copies measure the same and 16+ slightly worse.)
+constexpr int kWeightReplicas = 4;              // zero rows in front of every row matrix (>= largest dilation)
 
 // =====================================================================================================
 // Encoder (bf16, chunk-major output)
