@@ -26,11 +26,11 @@ using namespace ptx;
 
 constexpr int kC = 128;               // channels (bf16 path is specialised for the shipped width)
 constexpr int kKC = kC / 8;           // 16-byte pieces per row
-constexpr int kLead = 8;
+constexpr int kLead = 8;              // zero rows in front of every row matrix (>= largest dilation)
 // Every CTA of the fused kernel streams the same few hundred KB of layer weights at about the same time; CTA c reads replica
 // c % kWeightReplicas so that the reads spread over more L2 slices. (With per-slot rings 16 copies helped; with the shared ring,
 // the evict-last L2 policy and two producer threads 1-4 copies measure the same and 16+ slightly worse.)
-constexpr int kWeightReplicas = 4;              // zero rows in front of every row matrix (>= largest dilation)
+constexpr int kWeightReplicas = 4;
 
 // =====================================================================================================
 // Encoder (bf16, chunk-major output)
