@@ -798,9 +798,13 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
   int rc;
 
   static thread_local bool attr_set = false;
+  static thread_local size_t enc_attr_smem = 0;
   const size_t enc_smem = encode_smem_bytes(P, R, m->cfg.embed_dim);
-  if (!attr_set) {
+  if (enc_smem > enc_attr_smem) {
     DAN_CUDA_TRY(cudaFuncSetAttribute(encode_rows_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem));
+    enc_attr_smem = enc_smem;
+  }
+  if (!attr_set) {
     DAN_CUDA_TRY(cudaFuncSetAttribute(dan_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }

@@ -93,6 +93,10 @@ def run_case(name, cfg: DanConfig, batch: PileupBatch, seed: int):
 
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
+    only = sys.argv[1:]          # optional: names of the cases to (re)generate
+    global run_case
+    _run = run_case
+    run_case = lambda name, *a, **k: _run(name, *a, **k) if (not only or name in only) else None
     mixed = cat_batches([make_pileups(3, seed=11, coverage="poisson"), make_pileups(2, seed=12, coverage="full"),
                          make_pileups(1, seed=13, coverage="ragged")])
     # PROD topology, small FC trunk: mixed coverage + the hand-made corner cases
@@ -108,6 +112,8 @@ def main():
                                        final_layer_dilation=2, conv_1d_pool_layers=(1, 3), concat_hw_reads=False,
                                        skip_final_maxpool=True, use_strands=False, hidden_dropout=0.0),
              make_pileups(3, seed=41, coverage="poisson"), seed=5)
+    # BASELINE configs[3]: 300 read rows, ragged depth 1..300 (reference built with MAX_READS = num_single_reads = 300)
+    run_case("reads300_ragged", small_config(num_reads=300), make_pileups(3, seed=51, num_reads=300, coverage="ragged", max_depth=300), seed=6)
 
 
 if __name__ == "__main__":

@@ -73,6 +73,15 @@ def build_reference_model(cfg, state_dict=None, quiet=True):
     create_arg_parser, Basic2DNet = import_reference()
     args = create_arg_parser().parse_args(cfg_to_flags(cfg))
     sink = io.StringIO()
+    # A read axis other than 100 rows (BASELINE configs[3], up to 300): the reference sizes its pooling kernels from the module
+    # constant MAX_READS and its FC input from num_single_reads (model.py:194,303-304,336) — SURVEY App. F recipe.
+    import dl4vc.model as ref_model_module
+    extra = {}
+    if cfg.num_reads != 100:
+        ref_model_module.MAX_READS = cfg.num_reads
+        extra["num_single_reads"] = cfg.num_reads
+    else:
+        ref_model_module.MAX_READS = 100
     with (contextlib.redirect_stdout(sink) if quiet else contextlib.nullcontext()):
         model = Basic2DNet(
             target_size=3, init_conv_channels=args.model_init_conv_channels,
@@ -87,7 +96,7 @@ def build_reference_model(cfg, state_dict=None, quiet=True):
             bottleneck_channels=args.model_bottleneck_size, bottleneck_linear_outputs=args.model_bottleneck_size,
             concat_hw_reads=args.model_concat_hw_reads, use_naive_variant_encoding=args.model_use_naive_var_vector,
             use_reads_ref_var_mask=args.model_use_reads_ref_var_mask, append_allele_frequency=args.model_use_AF,
-            layer_sizes=list(cfg.layer_sizes), args=args)
+            layer_sizes=list(cfg.layer_sizes), args=args, **extra)
     if state_dict is not None:
         model.load_state_dict(state_dict)
     return model.eval(), args

@@ -10,7 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["prod_smallfc_mixed", "prod_smallfc_edge", "prod_full", "min_smallfc", "variant_a"]
+GOLDEN_CASES = ["prod_smallfc_mixed", "prod_smallfc_edge", "prod_full", "min_smallfc", "variant_a", "reads300_ragged"]
 
 
 def pytest_configure(config):

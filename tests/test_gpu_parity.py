@@ -82,7 +82,7 @@ def test_fp32_batch_split_invariance():
 # genotype argmax identical on every candidate whose reference margin exceeds the tolerance.
 # ---------------------------------------------------------------------------------------------------------
 BF16_TOL = 3e-2
-BF16_CASES = ["prod_smallfc_mixed", "prod_smallfc_edge", "prod_full", "variant_a"]
+BF16_CASES = ["prod_smallfc_mixed", "prod_smallfc_edge", "prod_full", "variant_a", "reads300_ragged"]
 
 
 @pytest.mark.parametrize("name", BF16_CASES)

