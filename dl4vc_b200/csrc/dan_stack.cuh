@@ -378,8 +378,10 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     const int g_begin = h == 0 ? 0 : 14, g_end = h == 0 ? 14 : 26;
     // x += pool (model.py:734-742: the read-axis mean of the previous layer's output is added to the input of this segment's first
     // layer). Runs on the freshly loaded read before the slot is handed to the issuer; bf16(x + pool) like the stand-alone kernel.
+    int tr_n = 0;
     auto add_pool = [&](int read_local, uint32_t parity) {
       mbar_wait(&sm->in_full[s], parity);
+      if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 7u << 24);     // the read has landed
       const long cand = (long)(r_begin + read_local) / p.reads_per_cand;
       const float* pl = p.pool + cand * kKC * p.P * 8;
       uint8_t* b = bufs + (size_t)s * kStkBuf + kStkLead * 16;
@@ -401,7 +403,6 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     if (p.pool && s < n_reads) add_pool(s, 0);
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
     uint32_t opc = 0, eops = 0;
-    int tr_n = 0;
     long long t_wait = 0, t_main = 0, t_bott = 0, t_io = 0, t0 = 0;
     const bool prof = prof_on && gtid == 0;
     for (int i = s; i < n_reads; i += 2) {
@@ -491,6 +492,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           // refill the slot as soon as the store has read the buffer
           if (gtid == 0) {
             bulk_wait_read0();
+            if (trace_on) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 6u << 24 | (eops & 0xFFFFu));     // the store has drained the buffer
             if (i + 2 < n_reads) load_read(i + 2);
           }
           if (p.pool && i + 2 < n_reads) add_pool(i + 2, (uint32_t)((i + 2) >> 1) & 1u);
