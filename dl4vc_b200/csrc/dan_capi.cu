@@ -48,6 +48,17 @@ void dan_set_error(const char* fmt, ...) {
 }
 void dan_count_launch(int n) { g_launches += n; }
 
+// scores[b] = {1 - softmax(xbinary)[0], softmax(xVT)[0..2]}  (trainer.py:611-623); one thread per candidate
+__global__ void dan_scores_kernel(const float* __restrict__ heads, int batch, float4* __restrict__ scores) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const float* h = heads + (long)b * DAN_NUM_HEAD_OUTPUTS;
+  const float b0 = h[0], b1 = h[1], v0 = h[2], v1 = h[3], v2 = h[4];
+  const float mb = fmaxf(b0, b1), e0 = expf(b0 - mb), e1 = expf(b1 - mb);
+  const float mv = fmaxf(v0, fmaxf(v1, v2)), f0 = expf(v0 - mv), f1 = expf(v1 - mv), f2 = expf(v2 - mv), inv = 1.f / (f0 + f1 + f2);
+  scores[b] = make_float4(1.f - e0 / (e0 + e1), f0 * inv, f1 * inv, f2 * inv);
+}
+
 extern "C" {
 
 const char* dan_last_error(void) { return g_error; }
@@ -277,6 +288,17 @@ int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, cons
   if (batch == 0) return DAN_OK;
   DevInputs in{reads, q_scores, strands, ref, ref_masks, var_masks};
   return dan_fp32_encode_reference_order(m, in, batch, x0_out, static_cast<cudaStream_t>(stream));
+}
+
+int dan_scores(const float* heads, int batch, float* scores_out, void* stream) {
+  if (batch < 0) { dan_set_error("negative batch"); return DAN_E_INVALID; }
+  if (batch == 0) return DAN_OK;
+  if (!heads || !scores_out) { dan_set_error("heads / scores pointer is null"); return DAN_E_INVALID; }
+  if (reinterpret_cast<uintptr_t>(scores_out) & 15) { dan_set_error("scores_out must be 16-byte aligned"); return DAN_E_INVALID; }
+  dan_scores_kernel<<<(batch + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(heads, batch, reinterpret_cast<float4*>(scores_out));
+  dan_count_launch(1);
+  DAN_CUDA_TRY(cudaGetLastError());
+  return DAN_OK;
 }
 
 int dan_debug_fc_input(dan_model* m, int precision, int batch, const void* workspace, float* out, void* stream) {

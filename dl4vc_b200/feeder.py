@@ -6,6 +6,7 @@ PinnedBatchFeeder  collates the loader's per-candidate dicts (the schema `dl4vc/
                    hands them to `Basic2DNet.forward_heads_host`, whose library side overlaps the H2D staging of a chunk
                    with the kernels of the previous one. Collating batch k+1 on the host overlaps the GPU work of batch k.
 scores_from_heads  the caller-side post-ops of `trainer.py:611-623`: softmax over xbinary / xVT and the variant score 1 - p0.
+scores_on_device   the same post-ops as one CUDA kernel behind the C-ABI (`dan_scores`): 4 floats per candidate leave the GPU.
 format_vcf_info    the `BP=..;NV=..;HV=..;OV=..` field `utils.append_vcf_records` splices into VCF column 3 (`utils.py:162-178`).
 """
 from __future__ import annotations
@@ -100,6 +101,23 @@ def scores_from_heads(heads: torch.Tensor):
     xbinary, xvt = heads[:, 0:2], heads[:, 2:5]
     bin_score = 1.0 - torch.softmax(xbinary, dim=1)[:, 0]
     return bin_score, torch.softmax(xvt, dim=1)
+
+
+def scores_on_device(heads: torch.Tensor) -> torch.Tensor:
+    """Device version of `scores_from_heads` through the C-ABI (`dan_scores`, include/dan_b200.h): (B,27) CUDA head matrix ->
+    (B,4) CUDA tensor [bin_score, P(no variant), P(het), P(hom)], so only 16 bytes per candidate cross PCIe on the way to
+    the VCF writer. No CPU path: raises on a CPU tensor."""
+    from . import _lib
+    if not heads.is_cuda:
+        raise RuntimeError("scores_on_device needs the CUDA head matrix written by forward_heads (no CPU path)")
+    if heads.dim() != 2 or heads.shape[1] != 27 or heads.dtype != torch.float32:
+        raise RuntimeError("heads must be (B, 27) float32")
+    heads = heads.contiguous()
+    out = torch.empty((heads.shape[0], 4), dtype=torch.float32, device=heads.device)
+    with torch.cuda.device(heads.device):
+        _lib.check(_lib.load_library().dan_scores(heads.data_ptr(), heads.shape[0], out.data_ptr(),
+                                                   torch.cuda.current_stream().cuda_stream), "dan_scores")
+    return out
 
 
 def format_vcf_info(bin_score, vt_probs):

@@ -123,6 +123,14 @@ int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const ui
                      const uint8_t* var_masks, int batch, float* heads_out_host, void* workspace,
                      size_t workspace_bytes, void* stream);
 
+/* Replaces the caller-side score post-ops of trainer.test (dl4vc/trainer.py:611-623, use_var_type_threshold off) on the
+ * device, so that only 4 floats per candidate have to cross PCIe when the caller writes VCF records:
+ * scores_out[b] = { 1 - softmax(xbinary)[0],  softmax(xVT)[0], softmax(xVT)[1], softmax(xVT)[2] }
+ * (variant score, P{no variant}, P{het}, P{hom}; the BP / NV / HV / OV fields of dl4vc/utils.py:162-178).
+ * heads: batch*27 fp32 as written by dan_forward, scores_out: batch*4 fp32, both DEVICE pointers. */
+#define DAN_NUM_SCORE_OUTPUTS 4
+int dan_scores(const float* heads, int batch, float* scores_out, void* stream);
+
 /* Test hook for the bit-exact integer/encoding work (dl4vc/model.py:450-627,719): writes the conv-1 input in the
  * reference's logical order (batch, Cin, num_reads, read_len) fp32, DEVICE pointer. */
 int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,

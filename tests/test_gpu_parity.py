@@ -242,6 +242,23 @@ def test_bf16_layerwise_fallback_agrees_with_fused_path(monkeypatch):
     assert rel_err(layerwise, fused) < BF16_TOL
 
 
+def test_scores_on_device_match_trainer_post_ops():
+    """dan_scores (device) vs the reference's caller-side post-ops (trainer.py:611-623: softmax, 1 - p0), incl. extreme logits."""
+    from dl4vc_b200.feeder import scores_from_heads, scores_on_device
+    gen = torch.Generator().manual_seed(3)
+    heads = torch.randn((1000, 27), generator=gen) * 4
+    heads[0, :5] = torch.tensor([80.0, -80.0, 50.0, -50.0, 0.0])      # saturated softmax must stay finite
+    heads[1, :5] = torch.tensor([-80.0, 80.0, -90.0, -90.0, -90.0])
+    got = scores_on_device(heads.cuda()).cpu()
+    bin_score, vt = scores_from_heads(heads.double())
+    want = torch.cat([bin_score[:, None], vt], dim=1).float()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() < 2e-6
+    assert scores_on_device(torch.empty((0, 27), device="cuda")).shape == (0, 4)
+    with pytest.raises(RuntimeError):
+        scores_on_device(heads)
+
+
 def test_capi_rejects_bad_calls():
     """Error behaviour of the C-ABI: status codes + dan_last_error text, never a crash."""
     import ctypes as C
