@@ -619,7 +619,8 @@ struct Bf16Plan {
 Bf16Plan make_plan(const dan_model* m, int batch) {
   Bf16Plan pl{};
   pl.S = m->pass_candidates < batch ? m->pass_candidates : (batch > 0 ? batch : 1);
-  pl.Bc = batch < 1024 ? (batch > 0 ? batch : 1) : 1024;
+  const int fc_chunk = dan_bf16_fc_chunk(m);
+  pl.Bc = batch < fc_chunk ? (batch > 0 ? batch : 1) : fc_chunk;
   pl.BcPad = round_up_i(pl.Bc, 128);
   pl.rows = m->geom.rows_of(pl.S);
   pl.rowsPad = (pl.rows + 127) / 128 * 128;

@@ -201,12 +201,15 @@ int dan_forward(dan_model* m, int precision, const uint8_t* reads, const uint8_t
 }
 
 // ---- host-buffer entry point: chunked, double-buffered H2D staging on a side stream (north_star item 4) -------------------
-// The batch is cut into chunks of kHostChunk candidates. Chunk k+1 is copied from the caller's (pinned) host buffers into staging
+// The batch is cut into chunks of host_chunk() candidates. Chunk k+1 is copied from the caller's (pinned) host buffers into staging
 // buffer (k+1)&1 on the model's copy stream while chunk k runs on the caller's stream; events order copy -> compute and
 // compute -> reuse of the staging buffer. Only the first chunk's copy is exposed.
-static const int kHostChunk = 1024;   // = the FC trunk's chunk: the 151 MB FC1 weight stream is read once per 1024 candidates either way
 static const int kHostFirst = 128;
-static int host_chunk(int batch) { return batch < kHostChunk ? (batch > 0 ? batch : 1) : kHostChunk; }
+// staging chunk = the FC trunk's chunk (bf16: a whole number of conv-stack passes, ~1024 candidates; the 151 MB FC1 weight stream is read once per chunk either way)
+static int host_chunk(const dan_model* m, int batch, int precision) {
+  const int full = precision == DAN_PRECISION_BF16 ? dan_bf16_fc_chunk(m) : 1024;
+  return batch < full ? (batch > 0 ? batch : 1) : full;
+}
 static size_t host_stage_bytes_chunk(const dan_model* m, int chunk) {
   const size_t tile = (size_t)chunk * m->P * m->R, vec = (size_t)chunk * m->P;
   return 3 * round_up_z(tile, 256) + 3 * round_up_z(vec, 256);
@@ -214,7 +217,7 @@ static size_t host_stage_bytes_chunk(const dan_model* m, int chunk) {
 
 size_t dan_workspace_bytes_host(const dan_model* m, int batch, int precision) {
   if (!m || batch < 0) return 0;
-  const int chunk = host_chunk(batch);
+  const int chunk = host_chunk(m, batch, precision);
   return round_up_z(dan_workspace_bytes(m, chunk, precision), 256) + 2 * host_stage_bytes_chunk(m, chunk) +
          round_up_z((size_t)(batch > 0 ? batch : 1) * DAN_NUM_HEAD_OUTPUTS * 4, 256);
 }
@@ -226,7 +229,7 @@ int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const ui
   int rc = check_forward_args(m, precision, reads, q_scores, strands, ref, ref_masks, var_masks, batch, heads_out_host);
   if (rc) return rc;
   if (batch == 0) return DAN_OK;
-  const int chunk = host_chunk(batch);
+  const int chunk = host_chunk(m, batch, precision);
   const size_t core = round_up_z(dan_workspace_bytes(m, chunk, precision), 256);
   const size_t stage_b = host_stage_bytes_chunk(m, chunk);
   if (!workspace || workspace_bytes < dan_workspace_bytes_host(m, batch, precision)) { dan_set_error("workspace too small for host staging"); return DAN_E_WORKSPACE; }

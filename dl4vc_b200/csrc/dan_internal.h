@@ -93,6 +93,14 @@ int dan_fp32_pack(dan_model* m, const dan_weights* w, cudaStream_t st);
 void dan_fp32_free(dan_model* m);
 
 // bf16 tcgen05 path (dan_bf16.cu)
+// Candidates per FC-trunk chunk of the bf16 path: the whole number of conv-stack passes closest to 1024 candidates (PROD: 7 x 148 =
+// 1036), so that a large batch is cut into full passes only (no ragged last pass per chunk). The 151 MB FC1 weight matrix is streamed once per chunk.
+inline int dan_bf16_fc_chunk(const dan_model* m) {
+  const int S = m->pass_candidates;
+  if (S >= 1024) return S;
+  const int n = (1024 + S / 2) / S;
+  return (n < 1 ? 1 : n) * S;
+}
 size_t dan_bf16_workspace_bytes(const dan_model* m, int batch);
 int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_out, void* ws, size_t ws_bytes,
                      cudaStream_t st);
