@@ -133,7 +133,7 @@ def test_bf16_matches_fp32_path_on_a_larger_batch():
 
 def test_host_path_matches_device_path_across_chunks():
     """dan_forward_host (chunked, double-buffered H2D on a side stream) returns exactly what dan_forward returns on resident inputs;
-    2100 candidates = staging chunks of 128 + 1024 + 948, pinned and pageable host tensors."""
+    2100 candidates = staging chunks of 128 + 1036 + 936, pinned and pageable host tensors."""
     cfg = small_config()
     sd = synth_state_dict(cfg, seed=9)
     base = make_pileups(100, seed=321, coverage="poisson")
@@ -240,6 +240,42 @@ def test_bf16_layerwise_fallback_agrees_with_fused_path(monkeypatch):
     layerwise = _heads(model, g["arrays"])
     assert rel_err(layerwise, g["heads"]) < BF16_TOL
     assert rel_err(layerwise, fused) < BF16_TOL
+
+
+def test_main_py_call_sequence_dataparallel_checkpoint():
+    """The callers' contract: main.py:99-124 builds the module with its keyword set, wraps it in nn.DataParallel(...).cuda()
+    and loads a checkpoint whose keys carry the `module.` prefix; trainer.py:520-528,569-572 hands forward() CPU int64 tensors under
+    torch.no_grad(). The same sequence on the drop-in must reproduce the reference goldens; a later load_state_dict (new parameters)
+    must be picked up by the native weight store."""
+    from dl4vc_b200.factory import ctor_kwargs
+    from dl4vc_b200.model import Basic2DNet
+    g = load_golden("prod_smallfc_mixed")
+    cfg = g["cfg"]
+    sd = synth_state_dict(cfg, seed=g["seed"])
+    model = Basic2DNet(**ctor_kwargs(cfg))
+    assert sum(p.numel() for p in model.parameters()) > 0                                   # main.py:114
+    model = torch.nn.DataParallel(model).cuda()                                             # main.py:117
+    model.load_state_dict({"module." + k: v for k, v in sd.items()})                        # main.py:123-124
+    model.eval()                                                                            # trainer.py:476
+    model.module.set_precision("fp32")
+    r, q, s, ref, rm, vm = (t.long() for t in _tensors(g["arrays"]))                        # trainer.py:520-528 (CPU int64)
+    B = r.shape[0]
+    dummy = torch.zeros(B, dtype=torch.long)
+    with torch.no_grad():
+        out = model(r, ref, q, s, dummy, dummy, dummy, dummy, rm, vm)                       # trainer.py:569-572
+    assert len(out) == 14
+    got = torch.cat(out[:6], dim=1).cpu().numpy()
+    assert rel_err(got, g["heads"]) < FP32_TOL
+    assert set(model.state_dict().keys()) == {"module." + k for k in sd}                    # main.py:196 (checkpoint save)
+    # new parameters -> new native weights
+    sd2 = synth_state_dict(cfg, seed=g["seed"] + 1)
+    model.load_state_dict({"module." + k: v for k, v in sd2.items()})
+    with torch.no_grad():
+        out2 = model(r, ref, q, s, dummy, dummy, dummy, dummy, rm, vm)
+    got2 = torch.cat(out2[:6], dim=1).cpu().numpy()
+    fresh = build_model(cfg, sd2, precision="fp32")
+    assert np.array_equal(got2, _heads(fresh, g["arrays"]))
+    assert not np.allclose(got2, got)
 
 
 def test_scores_on_device_match_trainer_post_ops():
