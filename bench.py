@@ -54,7 +54,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int, period_s: float = 0.1):
         super().__init__(daemon=True)
         self.index, self.period = index, period_s
-        self.samples, self.reasons = [], set()
+        self.samples, self.reasons, self.power = [], set(), []
         self.max_mhz = None
         self._halt = threading.Event()
         self.ok = False
@@ -83,6 +83,10 @@ class ClockSampler(threading.Thread):
             try:
                 self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
                 try:
+                    self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
+                except Exception:
+                    pass
+                try:
                     r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
                 except Exception:
                     r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
@@ -99,7 +103,9 @@ class ClockSampler(threading.Thread):
             self.join(timeout=2)
         s = sorted(self.samples)
         med = s[len(s) // 2] if s else None
-        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s)}
+        pw = sorted(self.power)
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(s),
+                "power_w": round(pw[len(pw) // 2], 1) if pw else None}
 
 
 # ---------------------------------------------------------------------------------------------------------
