@@ -304,6 +304,22 @@ int dan_scores(const float* heads, int batch, float* scores_out, void* stream) {
   return DAN_OK;
 }
 
+int dan_format_vcf_info(const float* scores, int n, char* out, size_t out_bytes) {
+  if (n < 0) { dan_set_error("negative record count"); return DAN_E_INVALID; }
+  if (n == 0) return DAN_OK;
+  if (!scores || !out) { dan_set_error("scores / out pointer is null"); return DAN_E_INVALID; }
+  if (out_bytes < (size_t)n * DAN_VCF_INFO_STRIDE) { dan_set_error("output buffer too small: need %zu bytes", (size_t)n * DAN_VCF_INFO_STRIDE); return DAN_E_INVALID; }
+  for (int i = 0; i < n; ++i) {
+    const float* s4 = scores + (size_t)i * DAN_NUM_SCORE_OUTPUTS;
+    for (int j = 0; j < 4; ++j)
+      if (!(s4[j] >= 0.f && s4[j] <= 1.f)) { dan_set_error("score %d of record %d is not a probability", j, i); return DAN_E_INVALID; }
+    // python's '%.8f' % float32 widens to double first (utils.py:171-176); printf rounds the same way (correctly rounded decimal)
+    snprintf(out + (size_t)i * DAN_VCF_INFO_STRIDE, DAN_VCF_INFO_STRIDE, "BP=%.8f;NV=%.8f;HV=%.8f;OV=%.8f",
+             (double)s4[0], (double)s4[1], (double)s4[2], (double)s4[3]);
+  }
+  return DAN_OK;
+}
+
 int dan_debug_fc_input(dan_model* m, int precision, int batch, const void* workspace, float* out, void* stream) {
   if (!m || !workspace || !out || batch < 1) { dan_set_error("bad argument"); return DAN_E_INVALID; }
   cudaStream_t st = static_cast<cudaStream_t>(stream);

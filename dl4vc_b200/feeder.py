@@ -127,6 +127,21 @@ def format_vcf_info(bin_score, vt_probs):
     return ["BP=%.8f;NV=%.8f;HV=%.8f;OV=%.8f" % (b[i], v[i, 0], v[i, 1], v[i, 2]) for i in range(len(b))]
 
 
+def format_vcf_info_native(scores) -> list:
+    """Same strings as `format_vcf_info` from a (B,4) float32 score matrix [bin_score, P(no variant), P(het), P(hom)] (the output of
+    `scores_on_device`, copied to the host), formatted by the C-ABI's `dan_format_vcf_info` instead of a Python loop."""
+    import ctypes as C
+    from . import _lib
+    arr = np.ascontiguousarray(np.asarray(scores, dtype=np.float32))
+    if arr.ndim != 2 or arr.shape[1] != 4:
+        raise RuntimeError("scores must be (B, 4)")
+    n, stride = arr.shape[0], 56
+    buf = C.create_string_buffer(max(n, 1) * stride)
+    _lib.check(_lib.load_library().dan_format_vcf_info(arr.ctypes.data, n, C.addressof(buf), len(buf)), "dan_format_vcf_info")
+    raw = buf.raw
+    return [raw[i * stride:i * stride + 55].decode("ascii") for i in range(n)]
+
+
 def splice_vcf_records(vcf_records, bin_score, vt_probs):
     """Records with the score field spliced in, one per line, as append_vcf_records would append them (utils.py:166-178)."""
     info = format_vcf_info(bin_score, vt_probs)

@@ -131,6 +131,13 @@ int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const ui
 #define DAN_NUM_SCORE_OUTPUTS 4
 int dan_scores(const float* heads, int batch, float* scores_out, void* stream);
 
+/* Replaces the per-record string formatting of utils.append_vcf_records (dl4vc/utils.py:171-176) for a batch: for each of the n
+ * rows of `scores` (HOST pointer, n*4 fp32 as written by dan_scores) writes the fixed-width, NUL-terminated text
+ * "BP=%.8f;NV=%.8f;HV=%.8f;OV=%.8f" at out + i*DAN_VCF_INFO_STRIDE (HOST buffer of n*DAN_VCF_INFO_STRIDE bytes). Values are
+ * probabilities in [0, 1], so every field is 10 characters and a record is 55 characters + NUL. Pure host code (no CUDA call). */
+#define DAN_VCF_INFO_STRIDE 56
+int dan_format_vcf_info(const float* scores, int n, char* out, size_t out_bytes);
+
 /* Test hook for the bit-exact integer/encoding work (dl4vc/model.py:450-627,719): writes the conv-1 input in the
  * reference's logical order (batch, Cin, num_reads, read_len) fp32, DEVICE pointer. */
 int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,

@@ -59,3 +59,21 @@ def test_vcf_info_field_matches_reference_writer(tmp_path):
         f.write_text("")
         utils.append_vcf_records(str(f), list(b), list(v), recs)
         assert f.read_text().splitlines() == lines
+
+
+def test_native_vcf_info_formatting_matches_python():
+    """dan_format_vcf_info (host code in the C-ABI library, no GPU needed) against the reference's '%.8f' formatting (utils.py:171-176)."""
+    from dl4vc_b200.feeder import format_vcf_info, format_vcf_info_native
+    rng = np.random.default_rng(5)
+    s = rng.random((2000, 4)).astype(np.float32)
+    s[0] = [0.0, 1.0, 0.0, 0.0]
+    s[1] = [1.0, 0.0, 1.0, 0.0]
+    s[2] = [0.999999995, 5e-9, 0.123456785, 0.5]          # rounding at the 8th decimal
+    want = format_vcf_info(s[:, 0], s[:, 1:])
+    got = format_vcf_info_native(s)
+    assert got == want
+    assert all(len(x) == 55 for x in got)
+    assert format_vcf_info_native(np.zeros((0, 4), np.float32)) == []
+    import pytest
+    with pytest.raises(RuntimeError):
+        format_vcf_info_native(np.full((1, 4), 1.5, np.float32))
