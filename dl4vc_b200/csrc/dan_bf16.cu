@@ -798,27 +798,18 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
   };
   int rc;
 
-  static thread_local bool attr_set = false;
-  static thread_local size_t enc_attr_smem = 0;
+  static DanSmemAttr enc_attr, layer_attr, stack_attr[4];
   const size_t enc_smem = encode_smem_bytes(P, R, m->cfg.embed_dim);
-  if (enc_smem > enc_attr_smem) {
-    DAN_CUDA_TRY(cudaFuncSetAttribute(encode_rows_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)enc_smem));
-    enc_attr_smem = enc_smem;
-  }
-  if (!attr_set) {
-    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_layer_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  DAN_CUDA_TRY(enc_attr.ensure(encode_rows_bf16_kernel, enc_smem));
+  DAN_CUDA_TRY(layer_attr.ensure(dan_layer_kernel, 227 * 1024));
   bool fused = m->P == 201 && m->geom.gap <= kStkLead && (!m->cfg.highway || bott == 32 || bott == 64) && !getenv("DAN_B200_LAYERWISE");
   for (int l = 1; l < L; ++l)      // a residual layer fed by a pool-add needs the un-pooled input as residual (model.py:732 vs :742)
     if (m->cfg.is_residual[l] && m->cfg.pool_after[l - 1]) fused = false;
-  static thread_local bool stack_attr_set = false;
-  if (fused && !stack_attr_set) {
-    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
-    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
-    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
-    DAN_CUDA_TRY(cudaFuncSetAttribute(dan_stack_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kStkSmemBytes));
-    stack_attr_set = true;
+  if (fused) {
+    DAN_CUDA_TRY(stack_attr[0].ensure(dan_stack_kernel<0>, kStkSmemBytes));
+    DAN_CUDA_TRY(stack_attr[1].ensure(dan_stack_kernel<1>, kStkSmemBytes));
+    DAN_CUDA_TRY(stack_attr[2].ensure(dan_stack_kernel<2>, kStkSmemBytes));
+    DAN_CUDA_TRY(stack_attr[3].ensure(dan_stack_kernel<3>, kStkSmemBytes));
   }
   // layer-wise path: halo rows (and the rows past the last tile) must read as zero: clear the row matrices once per call.
   // The fused path loads and stores exactly the P data rows of every read and keeps its zero rows in shared memory.

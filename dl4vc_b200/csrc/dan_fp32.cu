@@ -411,11 +411,8 @@ static EncodeParams make_encode_params(const dan_model* m, const DevInputs& in) 
 
 static int launch_encode_fp32(const dan_model* m, const DevInputs& in, long cand0, int cands, float* rows, cudaStream_t st) {
   const size_t smem = encode_smem_bytes(m->P, m->R, m->cfg.embed_dim);
-  static thread_local size_t attr_smem = 0;          // models with different read counts share the process
-  if (smem > attr_smem) {
-    DAN_CUDA_TRY(cudaFuncSetAttribute(encode_rows_fp32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  static DanSmemAttr attr;          // models with different read counts share the process
+  DAN_CUDA_TRY(attr.ensure(encode_rows_fp32_kernel, smem));
   encode_rows_fp32_kernel<<<cands, 256, smem, st>>>(make_encode_params(m, in), cand0, rows);
   dan_count_launch();
   DAN_CUDA_TRY(cudaGetLastError());

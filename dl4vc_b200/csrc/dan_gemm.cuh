@@ -201,11 +201,8 @@ struct Gemm2Operand { const void* base; long rows; long row_stride_bytes; long b
 
 template <int BN>
 int g2_launch(const CUtensorMap& ma, const CUtensorMap& mb, const Gemm2Params& g, cudaStream_t st) {
-  static thread_local bool attr = false;
-  if (!attr) {
-    DAN_CUDA_TRY(cudaFuncSetAttribute(tma_gemm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g2_smem_bytes<BN>()));
-    attr = true;
-  }
+  static DanSmemAttr attr;
+  DAN_CUDA_TRY(attr.ensure(tma_gemm_kernel<BN>, g2_smem_bytes<BN>()));
   { DanProfScope ps(DAN_PROF_GEMM, st); tma_gemm_kernel<BN><<<g.m_tiles * g.n_tiles * g.splits * g.batch, kG2Threads, g2_smem_bytes<BN>(), st>>>(ma, mb, g); }
   dan_count_launch();
   DAN_CUDA_TRY(cudaGetLastError());

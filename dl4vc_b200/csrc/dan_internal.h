@@ -34,6 +34,27 @@ struct DanProfScope {
     }                                                                                           \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per function AND per device: remember, per call site, the largest size already set
+// on each device (a thread may move between devices, nn.DataParallel runs one thread per device) and raise it under a lock.
+struct DanSmemAttr {
+  std::mutex mu;
+  size_t set_bytes[64] = {};
+  template <class Kernel>
+  cudaError_t ensure(Kernel kernel, size_t bytes) {
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    std::lock_guard<std::mutex> lk(mu);
+    size_t& cur = set_bytes[dev & 63];
+    if (bytes > cur) {
+      e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+      if (e != cudaSuccess) return e;
+      cur = bytes;
+    }
+    return cudaSuccess;
+  }
+};
+
 // Row geometry of the activation matrices. Every per-read position is one row; reads are laid end to end with
 // `gap` all-zero rows after each read (gap = largest dilation), so a dilated tap is a plain row offset and the
 // zero padding of Conv2d(padding=(0,d)) (reference dl4vc/model.py:214-229) is implicit.
