@@ -408,9 +408,13 @@ __device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
 // loads in flight per thread of the pooling kernels: they run as one 64-thread CTA per SM beside the persistent stack kernel
 // (4096 spare registers per SM), so memory-level parallelism has to come from the thread itself
 constexpr int kPoolUnroll = 8;
+constexpr size_t kBmapBytesPerCand = (size_t)kStkBmapPerCand * 16;
 
 // pool[cand][c/8][p][c%8] = mean over reads (fp32)   (model.py:772)
-__global__ void __launch_bounds__(64) pool_mean_bf16_kernel(const uint4* __restrict__ h, long kstride, float* __restrict__ pool, RowGeom g) {
+// im2col (optional): the bf16 mean also goes out as the A operand of the pool-bias-map GEMM, row (cand*P + p'), columns tap*C + c holding
+// pool[c][p' + (tap-1)*dil] (zero outside the read: Conv2d zero padding, model.py:214-229)
+__global__ void __launch_bounds__(64) pool_mean_bf16_kernel(const uint4* __restrict__ h, long kstride, float* __restrict__ pool, RowGeom g,
+                                                            uint4* __restrict__ im2col = nullptr, int dil = 0) {
   const int cand = blockIdx.y, kc = blockIdx.z;
   const int pp = blockIdx.x * blockDim.x + threadIdx.x;
   if (pp >= g.P) return;
@@ -439,6 +443,46 @@ __global__ void __launch_bounds__(64) pool_mean_bf16_kernel(const uint4* __restr
   const float inv = 1.f / (float)g.R;
   dst[0] = make_float4(s[0] * inv, s[1] * inv, s[2] * inv, s[3] * inv);
   dst[1] = make_float4(s[4] * inv, s[5] * inv, s[6] * inv, s[7] * inv);
+  if (im2col) {
+    const uint4 v = make_uint4(pack_bf16x2(s[0] * inv, s[1] * inv), pack_bf16x2(s[2] * inv, s[3] * inv), pack_bf16x2(s[4] * inv, s[5] * inv), pack_bf16x2(s[6] * inv, s[7] * inv));
+    uint4* row0 = im2col + (long)cand * g.P * (3 * kKC) + kc;          // 3*kKC 16-byte pieces per row
+#pragma unroll
+    for (int tap = 0; tap < 3; ++tap) {
+      const int pd = pp - (tap - 1) * dil;                             // the output position that reads this value through `tap`
+      if (pd >= 0 && pd < g.P) row0[(long)pd * (3 * kKC) + tap * kKC] = v;
+    }
+    if (pp < dil) row0[(long)pp * (3 * kKC)] = make_uint4(0, 0, 0, 0);                          // tap 0 reaches in front of the read
+    if (pp >= g.P - dil) row0[(long)pp * (3 * kKC) + 2 * kKC] = make_uint4(0, 0, 0, 0);         // tap 2 reaches behind it
+  }
+}
+
+// ---- pool bias map (fused stack path). The read-mean pool-add in front of a conv layer (model.py:734-742) is linear:
+//   conv(x + pool) + b = conv(x) + [conv(pool) + b],
+// and the bracket is the same for all reads of a candidate. It is computed once per candidate on the tensor cores (tma_gemm over the
+// im2col rows above) and stored as bf16 pairs in exactly the order in which the stack kernel's epilogue threads hold the accumulator
+// (tcgen05.ld 16x256b fragments, dan_stack_epi.cuh): per candidate 8 roles (position half h, lane quadrant q) x 7 chunks of 16
+// positions x 32 lanes x 8 words; word gi*4 + j = channel 32q + 8j + lane/4, positions 8*(g0 + gi) + 2*(lane%4) + {0,1} with
+// g0 = (h ? 14 : 0) + 2*chunk. The layer's epilogue adds it instead of the per-channel bias; the per-read pool-add (103 KB of L2
+// reads and a 54 KB shared-memory read-modify-write on every read boundary) disappears.
+__global__ void bmap_pack_kernel(const float* __restrict__ gmap, const float* __restrict__ bias, uint4* __restrict__ out, int cands, int P) {
+  const long total = (long)cands * 8 * 7 * 32 * 2;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int half = (int)(i & 1), lane = (int)((i >> 1) & 31);
+    long t = i >> 6;
+    const int chunk = (int)(t % 7); t /= 7;
+    const int role = (int)(t % 8); const long cand = t / 8;
+    const int h = role >> 2, q = role & 3, g0 = (h ? 14 : 0) + 2 * chunk, gi = half;
+    uint32_t w[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = 32 * q + 8 * j + (lane >> 2), pos = 8 * (g0 + gi) + 2 * (lane & 3);
+      const float b = bias[c];
+      const float lo = pos < P ? gmap[(cand * P + pos) * kC + c] + b : 0.f;
+      const float hi = pos + 1 < P ? gmap[(cand * P + pos + 1) * kC + c] + b : 0.f;
+      w[j] = pack_bf16x2(lo, hi);
+    }
+    out[i] = make_uint4(w[0], w[1], w[2], w[3]);
+  }
 }
 
 // out = bf16(h + pool) on data rows, 0 on gap rows   (model.py:742)
@@ -552,6 +596,7 @@ __global__ void pack_conv_bf16_kernel(const float* __restrict__ w, uint4* __rest
 __global__ void pack_linear_bf16_kernel(const float* __restrict__ w, uint4* __restrict__ out, int N, int Npad, int K, int Kpad,
                                         int mode, int P, int C, int R, int bott, int L, int pooled, int skip_max) {
   // mode 0: identity columns. mode 1: FC1 feature permutation (see dan_bf16_forward). mode 2: compression (O, Cb, 1, P): k = ((c/8)*P + p)*8 + c%8
+  // mode 4: conv weight (Cout, C, 1, 3) with k = tap*C + cin
   const long total = (long)(Kpad / 8) * Npad * 8;
   for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
     const int j = (int)(i & 7); long t = i >> 3;
@@ -576,6 +621,8 @@ __global__ void pack_linear_bf16_kernel(const float* __restrict__ w, uint4* __re
         const int g = (int)(k / (P * 8)), rem = (int)(k % (P * 8));
         const int pp = rem / 8, c = g * 8 + rem % 8;
         src = (long)c * P + pp;                           // within row n: (c, p)
+      } else if (mode == 4) {
+        src = (k % C) * 3 + k / C;
       }
       v = w[(long)n * K + src];
     }
@@ -588,6 +635,7 @@ struct Bf16Weights {
   uint4* wconv[DAN_MAX_LAYERS]; uint4* wres[DAN_MAX_LAYERS]; uint4* wbott[DAN_MAX_LAYERS]; uint4* wcomp[DAN_MAX_LAYERS];
   uint4* wcomp_all;                   // all layers' compression weights, [L][bott][P*bott] bf16 (one batched GEMM operand)
   uint4* fcw[DAN_MAX_FC]; uint4* headw;
+  uint4* wbmap[DAN_MAX_LAYERS];       // layers fed by a read-mean pool-add: conv weight as a row-major GEMM operand [cout][tap*C + cin] bf16 (pool bias map)
   const float** comp_bias_ptrs;       // device array of L pointers
   uint8_t* wstream[DAN_MAX_LAYERS];   // conv | residual | bottleneck operand images of a layer, contiguous (dan_stack.cuh); kWeightReplicas copies
   size_t wstream_bytes[DAN_MAX_LAYERS];   // bytes of one copy (256-byte multiple)
@@ -612,7 +660,7 @@ struct Bf16Plan {
   long hw_layer_stride;
   long t_layer_pieces;               // uint4 pieces of one layer's T matrix
   int fcKC;                          // FC input pieces
-  size_t off_zero_begin, off_x0, off_h[4], off_zero_end, off_t[2], off_pool[2], off_agree, off_hw[2], off_fcin, off_fcx[DAN_MAX_FC], total;
+  size_t off_zero_begin, off_x0, off_h[4], off_zero_end, off_t[2], off_pool[2], off_im2col, off_bmapg, off_bmap, off_agree, off_hw[2], off_fcin, off_fcx[DAN_MAX_FC], total;
   int maxN;
 };
 
@@ -637,6 +685,9 @@ Bf16Plan make_plan(const dan_model* m, int batch) {
   pl.t_layer_pieces = (long)m->P * (bott / 8) * pl.readsPad;
   for (int i = 0; i < 2; ++i) pl.off_t[i] = take((size_t)m->L * pl.t_layer_pieces * 16);       // two sets: passes k and k+1 are in flight together
   for (int i = 0; i < 2; ++i) pl.off_pool[i] = take((size_t)pl.S * m->P * kC * 4);
+  pl.off_im2col = take((size_t)pl.S * m->P * 3 * kC * 2);      // pool bias map (see bmap_pack_kernel): im2col of the read-mean, bf16 [cand*P + p][tap*C + c]
+  pl.off_bmapg = take((size_t)pl.S * m->P * kC * 4);          // conv(pool), fp32 [cand*P + p][cout]
+  pl.off_bmap = take((size_t)pl.S * kBmapBytesPerCand);      // conv(pool) + bias in the stack epilogue's fragment order, bf16 pairs
   pl.off_agree = take((size_t)pl.S * 2 * m->R);
   pl.hw_layer_stride = pl.readsPad * bott;
   for (int i = 0; i < 2; ++i) pl.off_hw[i] = take((size_t)m->L * pl.hw_layer_stride * 4);
@@ -694,6 +745,10 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
       if (bott_b) bw->wbott[l] = reinterpret_cast<uint4*>(bw->wstream[l] + conv_b + res_b);
     }
     pack_conv_bf16_kernel<<<grid_for((long)3 * kc_in * kC * 8), 256, 0, st>>>(w->conv_w[l], bw->wconv[l], cin, kc_in);
+    if (l > 0 && m->cfg.pool_after[l - 1]) {
+      if ((rc = alloc(&bw->wbmap[l], (size_t)kC * 3 * kC / 8))) return rc;
+      pack_linear_bf16_kernel<<<grid_for((long)3 * kC * kC), 256, 0, st>>>(w->conv_w[l], bw->wbmap[l], kC, kC, 3 * kC, 3 * kC, 4, P, kC, R, bott, L, 0, 0);
+    }
     if (m->cfg.is_residual[l]) {
       pack_linear_bf16_kernel<<<grid_for((long)kKC * kC * 8), 256, 0, st>>>(w->res_w[l], bw->wres[l], kC, kC, kC, kC, 3, P, kC, R, bott, L, 0, 0);
     }
@@ -777,6 +832,9 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
   uint4* H[4]; for (int i = 0; i < 4; ++i) H[i] = reinterpret_cast<uint4*>(base + pl.off_h[i]);
   uint4* Tset[2] = {reinterpret_cast<uint4*>(base + pl.off_t[0]), reinterpret_cast<uint4*>(base + pl.off_t[1])};
   float* POOLset[2] = {reinterpret_cast<float*>(base + pl.off_pool[0]), reinterpret_cast<float*>(base + pl.off_pool[1])};
+  uint4* IM2COL = reinterpret_cast<uint4*>(base + pl.off_im2col);
+  float* BMAPG = reinterpret_cast<float*>(base + pl.off_bmapg);
+  uint4* BMAP = reinterpret_cast<uint4*>(base + pl.off_bmap);
   uint4* T = Tset[0];
   float* POOL = POOLset[0];
   uint8_t* AGREE = reinterpret_cast<uint8_t*>(base + pl.off_agree);
@@ -816,12 +874,14 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
   if (!fused) DAN_CUDA_TRY(cudaMemsetAsync(base + pl.off_zero_begin, 0, pl.off_zero_end - pl.off_zero_begin, st));
 
   // one persistent launch of dan_stack_kernel over layers [l, l_end) of a pass (dan_stack.cuh)
+  bool seg_bmap = false;     // the next launch_segment takes the pool term from the bias map instead of adding the pool table to every read
   auto launch_segment = [&](int l, int l_end, const uint4* seg_in, uint4* next, int set, bool with_pool, int ns) -> int {
           StackParams sp{};
           sp.in = seg_in; sp.in_kstride = pl.kstride; sp.out = next; sp.out_kstride = pl.kstride;
           sp.t_reads_stride = pl.readsPad; sp.num_reads = ns * R; sp.P = P; sp.pitch = g.pitch; sp.bott = bott > 0 ? bott : 32;
           sp.num_layers = l_end - l;
-          sp.pool = with_pool ? POOLset[set] : nullptr; sp.reads_per_cand = R;
+          sp.pool = with_pool && !seg_bmap ? POOLset[set] : nullptr; sp.reads_per_cand = R;
+          sp.bmap = with_pool && seg_bmap ? BMAP : nullptr;
           for (int k = l; k < l_end; ++k) {
             StackLayer& SL = sp.layer[k - l];
             SL.wstream = bw->wstream[k]; SL.wreplica_stride = bw->wstream_bytes[k]; SL.chan = bw->chan_dev + (size_t)k * 4 * kC; SL.bbias = m->bottB[k];
@@ -979,8 +1039,22 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           uint4* next = H[(hsel + 1) % 3];
           if ((rc = launch_segment(l, l_end, cur, next, 0, with_pool, ns))) return rc;
           if (m->cfg.pool_after[l_end - 1] && l_end < L) {
-            { DanProfScope ps(DAN_PROF_POOL, st); pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(next, pl.kstride, POOL, g); }
+            static const bool no_bmap = getenv("DAN_B200_NO_BMAP") != nullptr;       // development: per-read pool-add instead of the bias map
+            seg_bmap = !no_bmap && bw->wbmap[l_end] != nullptr;
+            { DanProfScope ps(DAN_PROF_POOL, st);
+              pool_mean_bf16_kernel<<<dim3((P + 63) / 64, ns, kKC), 64, 0, st>>>(next, pl.kstride, POOL, g, seg_bmap ? IM2COL : nullptr, m->cfg.dilation[l_end]); }
             dan_count_launch();
+            if (seg_bmap) {
+              // bias map of layer l_end: conv(pool) on the tensor cores (rows = candidate positions, K = 3 taps x 128 channels), then + bias in fragment order
+              Gemm2Operand A{IM2COL, (long)ns * P, 3L * kC * 2, 0};
+              Gemm2Operand B{bw->wbmap[l_end], kC, 3L * kC * 2, 0};
+              Gemm2Params gp{};
+              gp.M = ns * P; gp.N = kC; gp.K = 3 * kC; gp.mode = kG2Raw; gp.out = BMAPG; gp.out_batch_stride = 0; gp.ldo = kC;
+              if ((rc = run_gemm2(A, B, gp, 1, bw->num_sms, st))) return rc;
+              { DanProfScope ps(DAN_PROF_POOL, st); bmap_pack_kernel<<<grid_for((long)ns * kStkBmapPerCand), 256, 0, st>>>(BMAPG, m->convB[l_end], BMAP, ns, P); }
+              dan_count_launch();
+              DAN_CUDA_TRY(cudaGetLastError());
+            }
           }
           cur = next; hsel = (hsel + 1) % 3;
           l = l_end;

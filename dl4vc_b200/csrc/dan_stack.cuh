@@ -38,6 +38,8 @@ constexpr int kStkStageBytes = 8192;   // weight-ring stage = two k-step blocks 
 constexpr int kStkStages = 14;         // stages of the weight ring shared by the two slots (>= largest op (12) + prefetch)
 constexpr int kStkMaxSeg = 8;          // layers per segment
 constexpr int kStkRegsIssue = 56, kStkRegsEpi = 104;   // setmaxnreg redistributes the launch allocation (640 x 96): 128 x 56 + 512 x 104 = 60416 <= 61440
+constexpr int kStkBmapChunk = 64;       // uint4 per (role, 16-position chunk) of the pool bias map: 32 lanes x 2 (bmap_pack_kernel, dan_bf16.cu)
+constexpr int kStkBmapPerCand = 8 * 7 * kStkBmapChunk;   // uint4 per candidate: 8 roles (position half, lane quadrant) x 7 chunks
 constexpr int kStkSmemHeader = 3072;   // barriers, TMEM pointer, bottleneck biases of the segment
 constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + kStkStages * kStkStageBytes;
 
@@ -58,6 +60,7 @@ struct StackParams {
   long t_reads_stride;
   int num_reads, P, pitch, bott, num_layers;
   const float* pool; int reads_per_cand;   // optional read-mean of the previous segment, fp32 [candidate][c/8][p][8]: added to every read on load (model.py:742)
+  const uint4* bmap;                   // optional pool bias map conv(pool) + bias of the segment's first layer (replaces `pool`), [candidate][kStkBmapPerCand]
   unsigned long long* prof;            // optional [grid][16] cycle counters (development aid), or null
   uint2* trace; int trace_cap;         // development: event trace of CTA 0 (id, clock), trace[0].x = count
   int debug;                           // development: bit 0 = skip the MMAs, bit 1 = skip epilogue math/stores
@@ -408,13 +411,28 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     for (int i = s; i < n_reads; i += 2) {
       for (int l = 0; l < p.num_layers; ++l) {
         const StackLayer& L = p.layer[l];
+        const bool with_bmap = l == 0 && p.bmap != nullptr;     // the conv bias arrives inside the per-candidate pool bias map
+        const bool last = l + 1 == p.num_layers;
+        // without a bottleneck the layer's main epilogue is the read's last op: when the next read still gets the pool table added in
+        // shared memory, the hand-over to the issuer has to wait for that (the issuer only waits for act_ready and the load)
+        const bool defer_ready = last && !L.highway && p.pool != nullptr;
         EpiConsts k;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = 32 * q + 8 * j + (lane >> 2);
-          const float b = __ldg(L.chan + c);
+          const float b = with_bmap ? 0.f : __ldg(L.chan + c);
           k.scale[j] = __ldg(L.chan + kC + c); k.rbias[j] = __ldg(L.chan + 3 * kC + c);
           k.c[j] = fmaf(k.scale[j], b, __ldg(L.chan + 2 * kC + c)); k.nb[j] = -b;
+        }
+        // pool bias map of this read's candidate, this thread's fragments: the first four chunks are requested before the
+        // accumulator is awaited (their L2 latency hides under the conv MMAs), the rest as the chunks are consumed
+        uint4 bpre[4][2];
+        const uint4* bm = nullptr;
+        if (with_bmap) {
+          const long cand = (long)(r_begin + i) / p.reads_per_cand;
+          bm = p.bmap + (cand * 8 + (h * 4 + q)) * (7 * kStkBmapChunk) + lane * 2;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { bpre[c][0] = __ldg(bm + c * kStkBmapChunk); bpre[c][1] = __ldg(bm + c * kStkBmapChunk + 1); }
         }
         if (prof) t0 = clock64();
         mbar_wait(&sm->acc_full[s], opc & 1);
@@ -423,11 +441,12 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 3u << 24 | (eops & 0xFFFFu));
         const bool do_epi = kDev == 0 || !(p.debug & 2);
         if (!do_epi) {}
+        else if (with_bmap) stack_epi_bmap(tbase, saddr0, lane, p.P, g_begin, (g_end - g_begin) / 2, k, bm, bpre);
         else if (L.residual) stack_epi_main<kEpiPreRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
         else stack_epi_main<kEpiFinal>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
         fence_proxy_async_smem();
         tc_fence_before();
-        mbar_arrive(&sm->act_ready[s]);
+        if (L.residual || !defer_ready) mbar_arrive(&sm->act_ready[s]);
         ++opc;
         if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
         if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
@@ -439,12 +458,11 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           if (do_epi) stack_epi_main<kEpiPostRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
           fence_proxy_async_smem();
           tc_fence_before();
-          mbar_arrive(&sm->act_ready[s]);
+          if (!defer_ready) mbar_arrive(&sm->act_ready[s]);
           ++opc;
           if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
           if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
         }
-        const bool last = l + 1 == p.num_layers;
         if (last) {
           // the segment output of this read is final: start writing it back now, under this layer's bottleneck MMA / epilogue
           named_bar_sync(1 + s, kStkEpiThreads);
@@ -496,7 +514,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             if (i + 2 < n_reads) load_read(i + 2);
           }
           if (p.pool && i + 2 < n_reads) add_pool(i + 2, (uint32_t)((i + 2) >> 1) & 1u);
-          if (L.highway) mbar_arrive(&sm->act_ready[s]);
+          if (L.highway || defer_ready) mbar_arrive(&sm->act_ready[s]);
           if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 5u << 24 | (eops & 0xFFFFu));
           if (prof) { const long long t1 = clock64(); t_io += t1 - t0; t0 = t1; }
         }

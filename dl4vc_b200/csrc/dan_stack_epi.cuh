@@ -109,6 +109,36 @@ __device__ __forceinline__ void stack_epi_main(uint32_t tbase, uint32_t saddr0, 
   if constexpr (MODE == kEpiPreRes) tmem_st_wait();
 }
 
+// Final epilogue with the per-candidate pool bias map (dan_bf16.cu bmap_pack_kernel) instead of the per-channel conv bias:
+// y = s * relu(z + B[c][p]) + t, B = conv(pool) + b as bf16 pairs in this thread's fragment order (word gi*4 + j of chunk c).
+// `pre` holds chunks 0..3 on entry; chunk c + 4 is requested as soon as chunk c has been read out of its registers.
+__device__ __forceinline__ void stack_epi_bmap(uint32_t tbase, uint32_t saddr0, int lane, int P, int g_begin, int nchunks, const EpiConsts& k,
+                                               const uint4* bm, uint4 (&pre)[4][2]) {
+#pragma unroll
+  for (int c = 0; c < 7; ++c) {
+    if (c < nchunks) {
+      const int g0 = g_begin + 2 * c;
+      uint32_t a0[8], a1[8];
+      stack_epi_load(tbase, g0, a0, a1);
+      const uint4 b0 = pre[c & 3][0], b1 = pre[c & 3][1];
+      if (c + 4 < nchunks) { pre[c & 3][0] = __ldg(bm + (c + 4) * kStkBmapChunk); pre[c & 3][1] = __ldg(bm + (c + 4) * kStkBmapChunk + 1); }
+      stack_epi_wait(a0, a1);
+      const uint32_t bw[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t* src = (j < 2) ? a0 : a1;
+          const int e = 4 * gi + 2 * (j & 1);
+          src[e] = __float_as_uint(__uint_as_float(src[e]) + bf16_lo(bw[gi * 4 + j]));
+          src[e + 1] = __float_as_uint(__uint_as_float(src[e + 1]) + bf16_hi(bw[gi * 4 + j]));
+        }
+      }
+      stack_epi_do<kEpiFinal>(a0, a1, tbase, saddr0, g0, lane, P, k);
+    }
+  }
+}
+
 // =====================================================================================================================
 // Pool epilogue: ALL 16 epilogue warps work on ONE accumulator (128 channels x 208 positions). Four warps share a TMEM
 // lane quadrant q (32 channels); warp w4 = 0..3 of the quadrant owns the 16-channel half hh = w4 & 1 and every second

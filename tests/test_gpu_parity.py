@@ -224,9 +224,26 @@ def test_feeder_end_to_end_matches_direct_forward():
         got.append(heads.numpy()); names += [m[0] for m in meta]
     got = np.concatenate(got)
     assert names == [f"chr1:{i}" for i in range(23)]
-    assert rel_err(got, want) < 1e-3           # same kernels; split-K atomics order may differ between batch shapes
+    # same kernels; the highway compression GEMM splits K when a pass has few tiles, so its fp32 summation order (and with it a handful
+    # of bf16 roundings of the FC input) depends on the batch shape — measured 1e-4 .. 1.3e-3; without the highway the two are bitwise equal
+    assert rel_err(got, want) < 4e-3
     b, v = scores_from_heads(torch.from_numpy(got))
     assert format_vcf_info(b.numpy(), v.numpy())[0].startswith("BP=")
+
+
+def test_bf16_pool_bias_map_is_batch_shape_invariant():
+    """The read-mean pool-add in front of layer 3 (model.py:734-742) enters the fused stack kernel as a per-candidate bias map
+    conv(pool) + b. Without the highway (whose split-K compression depends on the batch shape) the heads of a candidate must
+    not depend on the batch it arrives in — bitwise — and must stay within the bf16 bar of the fp32 path."""
+    cfg = small_config(highway=False)
+    model = build_model(cfg, synth_state_dict(cfg, seed=9), precision="fp32")
+    base = make_pileups(23, seed=11, coverage="poisson")
+    ref32 = _heads(model, base.arrays())
+    model.set_precision("bf16")
+    full = _heads(model, base.arrays())
+    parts = np.concatenate([_heads(model, base.slice(lo, min(lo + 10, 23)).arrays()) for lo in range(0, 23, 10)])
+    assert np.array_equal(full, parts)
+    assert np.abs(full - ref32).max() / np.abs(ref32).max() < BF16_TOL
 
 
 def test_bf16_layerwise_fallback_agrees_with_fused_path(monkeypatch):
