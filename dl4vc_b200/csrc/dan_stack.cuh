@@ -130,17 +130,19 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
 
-  // global -> shared load of local read i into its slot's buffer (one elected thread)
-  auto load_read = [&](int i) {
+  // global -> shared load of local read i into its slot's buffer, spread over the slot's 8 epilogue warps: lane 0 of warp wl moves
+  // chunk planes 2*wl and 2*wl + 1 and prefetches the same planes of the slot's next read into L2. A bulk-copy instruction costs its
+  // issuing thread ~170 cycles (and divergent lanes of one warp are serialised), so one thread issuing 2 x in_kc of them kept the
+  // slot waiting 5-6 k cycles at every read boundary. The barrier must be armed (arm_read) before any of the copies can complete.
+  auto arm_read = [&](int i) { mbar_expect_tx(&sm->in_full[i & 1], plane_bytes_in * in_kc); };
+  auto load_read_planes = [&](int i, int wl) {
     const int s = i & 1;
-    mbar_expect_tx(&sm->in_full[s], plane_bytes_in * in_kc);
     const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
     uint8_t* dst = bufs + (size_t)s * kStkBuf + kStkLead * 16;
     const uint64_t once = l2_policy_evict_first();          // activations stream through: read once, written once
-    for (int kc = 0; kc < in_kc; ++kc) bulk_g2s_hint(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s], once);
-    if (i + 2 < n_reads) {       // the slot's next read: pull it into L2 now so that its load (on the slot's critical path) is an L2 hit
-      const uint4* nxt = src + 2 * (long)p.pitch;
-      for (int kc = 0; kc < in_kc; ++kc) bulk_prefetch_l2(nxt + kc * p.in_kstride, plane_bytes_in);
+    for (int kc = 2 * wl; kc < 2 * wl + 2 && kc < in_kc; ++kc) {
+      bulk_g2s_hint(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s], once);
+      if (i + 2 < n_reads) bulk_prefetch_l2(src + 2 * (long)p.pitch + kc * p.in_kstride, plane_bytes_in);   // the next load becomes an L2 hit
     }
   };
 
@@ -402,7 +404,12 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       }
       fence_proxy_async_smem();
     };
-    if (gtid == 0 && s < n_reads) load_read(s);
+    const int wl = warp & 7;            // this warp's index within the slot's epilogue group
+    if (s < n_reads) {
+      if (gtid == 0) arm_read(s);
+      named_bar_sync(1 + s, kStkEpiThreads);
+      if (lane == 0) load_read_planes(s, wl);
+    }
     if (p.pool && s < n_reads) add_pool(s, 0);
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
     uint32_t opc = 0, eops = 0;
@@ -466,11 +473,11 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         if (last) {
           // the segment output of this read is final: start writing it back now, under this layer's bottleneck MMA / epilogue
           named_bar_sync(1 + s, kStkEpiThreads);
-          if (gtid == 0) {
+          if (lane == 0) {           // two chunk planes per warp (bulk groups are per thread: each issuer commits and later waits for its own)
             uint4* dst = p.out + kLead + (long)(r_begin + i) * p.pitch;
             const uint8_t* src = bufs + (size_t)s * kStkBuf + kStkLead * 16;
             const uint64_t once = l2_policy_evict_first();
-            for (int kc = 0; kc < kKC; ++kc) bulk_s2g_hint(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in, once);
+            for (int kc = 2 * wl; kc < 2 * wl + 2; ++kc) bulk_s2g_hint(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in, once);
             bulk_commit();
           }
         }
@@ -508,11 +515,11 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         if (last) {
           // every MMA of this read has completed (the last accumulator was awaited above) and the write-back has been issued:
           // refill the slot as soon as the store has read the buffer
-          if (gtid == 0) {
-            bulk_wait_read0();
-            if (trace_on) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 6u << 24 | (eops & 0xFFFFu));     // the store has drained the buffer
-            if (i + 2 < n_reads) load_read(i + 2);
-          }
+          if (lane == 0) bulk_wait_read0();                       // this warp's planes have been read out of the buffer
+          if (gtid == 0 && i + 2 < n_reads) arm_read(i + 2);
+          named_bar_sync(1 + s, kStkEpiThreads);                  // all planes drained, barrier armed
+          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 6u << 24 | (eops & 0xFFFFu));     // the store has drained the buffer
+          if (lane == 0 && i + 2 < n_reads) load_read_planes(i + 2, wl);
           if (p.pool && i + 2 < n_reads) add_pool(i + 2, (uint32_t)((i + 2) >> 1) & 1u);
           if (L.highway || defer_ready) mbar_arrive(&sm->act_ready[s]);
           if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 5u << 24 | (eops & 0xFFFFu));
@@ -520,7 +527,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         }
       }
     }
-    if (gtid == 0) bulk_wait0();
+    if (lane == 0) bulk_wait0();
     if (prof) { unsigned long long* d = p.prof + blockIdx.x * 16 + 2 + 3 * s; d[0] = t_wait; d[1] = t_main; d[2] = t_bott; p.prof[blockIdx.x * 16 + 8 + s] = t_io; }
   }
   tc_fence_before();

@@ -9,7 +9,7 @@ for line in open(path):
     ev.append((int(a, 16), int(b)))
 ev.sort(key=lambda x: x[1])
 t0 = ev[0][1]
-names = {1: "ISS_START", 2: "ISS_DONE", 3: "EPI_START", 4: "EPI_END", 5: "IO_DONE"}
+names = {1: "ISS_START", 2: "ISS_DONE", 3: "EPI_START", 4: "EPI_END", 5: "IO_DONE", 6: "STORE_DRAINED", 7: "READ_LANDED"}
 # ISS ids are 1-based op numbers, EPI ids 0-based: align to 0-based
 rows = []
 for i, t in ev:
