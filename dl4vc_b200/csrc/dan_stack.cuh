@@ -140,10 +140,12 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
     uint8_t* dst = bufs + (size_t)s * kStkBuf + kStkLead * 16;
     const uint64_t once = l2_policy_evict_first();          // activations stream through: read once, written once
-    for (int kc = 2 * wl; kc < 2 * wl + 2 && kc < in_kc; ++kc) {
+    for (int kc = 2 * wl; kc < 2 * wl + 2 && kc < in_kc; ++kc)
       bulk_g2s_hint(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s], once);
-      if (i + 2 < n_reads) bulk_prefetch_l2(src + 2 * (long)p.pitch + kc * p.in_kstride, plane_bytes_in);   // the next load becomes an L2 hit
-    }
+  };
+  auto prefetch_read_planes = [&](int i, int wl) {           // read i into L2, so that its load (on the slot's critical path) is an L2 hit
+    const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
+    for (int kc = 2 * wl; kc < 2 * wl + 2 && kc < in_kc; ++kc) bulk_prefetch_l2(src + kc * p.in_kstride, plane_bytes_in);
   };
 
   // register budget: the producer / issuer warpgroup (warps 16-19) hands registers to the four epilogue warpgroups
@@ -408,7 +410,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     if (s < n_reads) {
       if (gtid == 0) arm_read(s);
       named_bar_sync(1 + s, kStkEpiThreads);
-      if (lane == 0) load_read_planes(s, wl);
+      if (lane == 0) { load_read_planes(s, wl); if (s + 2 < n_reads) prefetch_read_planes(s + 2, wl); }
     }
     if (p.pool && s < n_reads) add_pool(s, 0);
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
@@ -522,6 +524,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           if (lane == 0 && i + 2 < n_reads) load_read_planes(i + 2, wl);
           if (p.pool && i + 2 < n_reads) add_pool(i + 2, (uint32_t)((i + 2) >> 1) & 1u);
           if (L.highway || defer_ready) mbar_arrive(&sm->act_ready[s]);
+          if (lane == 0 && i + 4 < n_reads) prefetch_read_planes(i + 4, wl);      // off the critical path: after the hand-over
           if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 5u << 24 | (eops & 0xFFFFu));
           if (prof) { const long long t1 = clock64(); t_io += t1 - t0; t0 = t1; }
         }
