@@ -298,9 +298,9 @@ def run_b200(args):
         "bound": "tensor", "kernel": "dan_stack_kernel (conv stack class)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if peak else None,
         # dram__bytes_read.sum + dram__bytes_write.sum of dan_stack_kernel from the committed `ncu --set full` capture
-        # (profiles/r01c_stack_kernel_ncu_full_summary.csv: 1.39 GB + 3.24 GB for the two segment launches of a 148-candidate pass),
-        # per launch like `achieved`
-        "traffic": 15.64e6 * B / dom_launches, "traffic_source": "ncu --set full, profiles/r01c (31.3 MB per candidate over both segment launches)",
+        # (profiles/r01e_stack_kernel_ncu_full_summary.csv: 1.384 GB + 2.500 GB for the two segment launches of a 148-candidate pass
+        # = 26.24 MB per candidate), averaged per launch like `achieved`
+        "traffic": 26.24e6 * B / dom_launches, "traffic_source": "ncu --set full, profiles/r01e (26.2 MB per candidate over both segment launches)",
         "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); burst {peaks['bf16_burst']}",
         "launches_per_step": dom_launches, "avg_launch_ms": dom_ms_step / dom_launches,
         "share_of_step": dom_ms_step / sum(cls_ms.values()) if sum(cls_ms.values()) > 0 else None,
