@@ -491,10 +491,18 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
           // bottleneck tile h: TMEM lane = position 128h + 32q + lane, columns = bottleneck channels
           const int c8n = p.bott / 8;
           const int pos = 128 * h + 32 * q + lane;
+          bool handed_over = false;
           for (int cc = 0; do_epi && cc < p.bott / 32; ++cc) {
             uint32_t r[32];
             tmem_ld32(tbase + (uint32_t)(h * p.bott + cc * 32), r);
             tmem_ld_wait();
+            if (!last && cc + 1 == p.bott / 32) {
+              // the accumulator has been read out: the next layer's conv MMAs (which overwrite these columns) may start while this
+              // thread still converts and stores its T rows
+              tc_fence_before();
+              mbar_arrive(&sm->act_ready[s]);
+              handed_over = true;
+            }
             if (pos < p.P) {
               const float* bb = &sm->bbias[l][cc * 32];
 #pragma unroll
@@ -509,7 +517,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             }
           }
           tc_fence_before();
-          if (!last) mbar_arrive(&sm->act_ready[s]);
+          if (!last && !handed_over) mbar_arrive(&sm->act_ready[s]);
           ++opc;
           if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
           if (prof) { const long long t1 = clock64(); t_bott += t1 - t0; t0 = t1; }
