@@ -230,7 +230,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       // slot 1 starts op n only after slot 0 has issued all of its op n: the tensor pipe then runs slot 1's MMAs under slot 0's
       // epilogue (and vice versa) instead of both slots computing and then both draining, and the lag between the two
       // consumers of the shared weight ring stays within one op (<= 12 of the 14 stages).
-      if (s == 1 && !(p.debug & 8)) { uint32_t spins = 0; while (*issued <= gops) { if (++spins > (1u << 28)) __trap(); } }
+      // (polled with a short sleep: a tight shared-memory spin would take issue slots from the epilogue warps of this warp's scheduler)
+      if (s == 1 && !(p.debug & 8)) { uint32_t spins = 0; while (*issued <= gops) { __nanosleep(32); if (++spins > (1u << 24)) __trap(); } }
       ++gops;
       mbar_wait(&sm->act_ready[s], opc & 1);
       if (first_of_read) mbar_wait(&sm->in_full[s], (uint32_t)k & 1);
