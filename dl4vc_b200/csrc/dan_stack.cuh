@@ -212,17 +212,28 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     long long t_dep = 0, t_wfull = 0;
     const bool do_mma = kDev == 0 || !(p.debug & 1);
     const bool no_w = kDev != 0 && (p.debug & 16);     // development: weights are not streamed (garbage operands, timing only)
+    // The full-barrier probe of an op's first stage(s) is issued BEFORE the op's dependencies are awaited (prewait*): a probe costs
+    // ~190 cycles even when the phase is complete, and there it would sit between the epilogue's hand-over and the op's first MMA.
+    bool prewaited = false;
     auto wait_w = [&]() {
+      if (prewaited) { prewaited = false; return; }
       if (no_w) return;
       if (prof_on) { const long long c0 = clock64(); mbar_wait(&wfull[wi], wp); t_wfull += clock64() - c0; }
       else mbar_wait(&wfull[wi], wp);
       tc_fence_after();
     };
     auto wait_w2 = [&](uint32_t wi1, uint32_t wp1) {
+      if (prewaited) { prewaited = false; return; }
       if (no_w) return;
       if (prof_on) { const long long c0 = clock64(); mbar_wait2(&wfull[wi], wp, &wfull[wi1], wp1); t_wfull += clock64() - c0; }
       else mbar_wait2(&wfull[wi], wp, &wfull[wi1], wp1);
       tc_fence_after();
+    };
+    auto prewait1 = [&]() { wait_w(); prewaited = true; };
+    auto prewait2 = [&]() {
+      const uint32_t wi1 = wi + 1 == kStkStages ? 0u : wi + 1, wp1 = wi1 == 0 ? wp ^ 1u : wp;
+      wait_w2(wi1, wp1);
+      prewaited = true;
     };
     auto adv2 = [&](uint32_t wi1, uint32_t wp1) { wi = wi1 + 1; wp = wp1; if (wi == kStkStages) { wi = 0; wp ^= 1; } };
     auto wait_dep = [&](bool first_of_read, int k) {
@@ -273,6 +284,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         const int residual = L.residual, highway = L.highway, ksteps = L.kc_in / 2, total = L.conv_blocks;
         const uint32_t dil = (uint32_t)L.dil;
         // ---- conv: D[cout][pos] = sum over taps and input-channel k-steps ----
+        if ((ksteps & 3) == 0) prewait2(); else prewait1();
         wait_dep(l == 0, k);
         if ((ksteps & 3) == 0) {
           // two ring stages (4 k-steps) per iteration: both full-barrier probes are in flight together and the four MMAs and
@@ -321,6 +333,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         op_done();
         // ---- residual 1x1: accumulates on x + b_res stored by the epilogue ----
         if (residual) {
+          prewait2();
           wait_dep(false, 0);
           uint32_t bd_lo = x_lo | b_lbo_x;
           for (int blk = 0; blk < kKC / 2; blk += 4) {
@@ -344,6 +357,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         }
         // ---- bottleneck 1x1, positions-as-M orientation: A = activation rows (two 128-row tiles), B = weights ----
         if (highway) {
+          prewait1();
           wait_dep(false, 0);
           uint32_t xa_lo = x_lo | b_lbo_x;
           for (int blk = 0; blk < kKC / 2; blk += bott_per_stage) {
