@@ -195,7 +195,20 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+        # stdout carries the ONE JSON line only: NCCL prints its version banner (and, at NCCL_DEBUG=INFO, its log) to fd 1 when the
+        # communicator is created, so fd 1 points at stderr until the first collective has run
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=dev)
+            warm = torch.zeros(1, device=dev)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     lib = _lib.load_library()     # fails loudly if the CUDA library is missing
     cfg = prod_config()
