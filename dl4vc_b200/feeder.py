@@ -6,6 +6,7 @@ PinnedBatchFeeder  collates the loader's per-candidate dicts (the schema `dl4vc/
                    hands them to `Basic2DNet.forward_heads_host`, whose library side overlaps the H2D staging of a chunk
                    with the kernels of the previous one. Collating batch k+1 on the host overlaps the GPU work of batch k.
 scores_from_heads  the caller-side post-ops of `trainer.py:611-623`: softmax over xbinary / xVT and the variant score 1 - p0.
+make_mask_vectors  batch proposal-mask decode of the loader (`dataset.py:112-250`) in the C-ABI library, pinned to the reference's outputs.
 scores_on_device   the same post-ops as one CUDA kernel behind the C-ABI (`dan_scores`): 4 floats per candidate leave the GPU.
 format_vcf_info    the `BP=..;NV=..;HV=..;OV=..` field `utils.append_vcf_records` splices into VCF column 3 (`utils.py:162-178`).
 """
@@ -125,6 +126,27 @@ def format_vcf_info(bin_score, vt_probs):
     b = np.asarray(bin_score, dtype=np.float64)
     v = np.asarray(vt_probs, dtype=np.float64)
     return ["BP=%.8f;NV=%.8f;HV=%.8f;OV=%.8f" % (b[i], v[i, 0], v[i, 1], v[i, 2]) for i in range(len(b))]
+
+
+def make_mask_vectors(ref_alleles, var_alleles, references, strict: bool = True):
+    """Batch version of the loader's `get_read_mask_vectors` (dl4vc/dataset.py:112-250) through the C-ABI (`dan_make_mask_vectors`):
+    REF / ALT strings of n VCF records + their encoded reference windows (n, 201) uint8 -> (ref_masks, var_masks, status), each mask
+    (n, 201) uint8. `status[i]` != 0 marks a record the reference itself would have raised on (masks all zero); with `strict` those
+    raise a RuntimeError like the reference's assert would."""
+    import ctypes as C
+    from . import _lib
+    refs = np.ascontiguousarray(np.asarray(references, dtype=np.uint8))
+    n = len(ref_alleles)
+    if refs.shape != (n, 201) or len(var_alleles) != n:
+        raise RuntimeError("references must be (n, 201) uint8 with one REF / ALT string per row")
+    xs = (C.c_char_p * max(n, 1))(*[str(a).encode("ascii") for a in ref_alleles])
+    ys = (C.c_char_p * max(n, 1))(*[str(a).encode("ascii") for a in var_alleles])
+    rm = np.zeros((n, 201), np.uint8); vm = np.zeros((n, 201), np.uint8); st = np.zeros(n, np.int32)
+    lib = _lib.load_library()
+    rc = lib.dan_make_mask_vectors(xs, ys, refs.ctypes.data, n, rm.ctypes.data, vm.ctypes.data, st.ctypes.data)
+    if rc != 0 and (strict or not st.any()):
+        _lib.check(rc, "dan_make_mask_vectors")
+    return rm, vm, st
 
 
 def format_vcf_info_native(scores) -> list:

@@ -138,6 +138,24 @@ int dan_scores(const float* heads, int batch, float* scores_out, void* stream);
 #define DAN_VCF_INFO_STRIDE 56
 int dan_format_vcf_info(const float* scores, int n, char* out, size_t out_bytes);
 
+/* Replaces the loader's per-item proposal-mask decode, get_read_mask_vectors + simple_variant_encoding_vectors
+ * (dl4vc/dataset.py:86-250), for a batch of n records: ref_alleles[i] / var_alleles[i] are the REF / ALT columns of the VCF record
+ * (NUL-terminated), references + i*201 the encoded 201-column reference window of the pileup (base_enum codes, '-' = 5).
+ * Writes ref_masks / var_masks (n*201 bytes each, HOST pointers): 0 everywhere except the allele's bases starting at the
+ * window's centre column (rewound past insert-gap columns), with the reference's conventions — deletes padded with '-' (5) in
+ * the variant mask, inserts with 'noinsert' (8) in the reference mask, ALT clipped to 51 bases, gap columns inside a deleted
+ * stretch left as "don't care" (0). status[i] (may be NULL) is 0 or the reason the reference itself would have raised for the
+ * record (DAN_MASK_E_*); masks of a failed record are all zero. Returns DAN_OK when every record decoded, DAN_E_INVALID otherwise.
+ * Pure host code (no CUDA call). */
+enum { DAN_MASK_OK = 0, DAN_MASK_E_ALLELE_CHAR = 1,   /* character outside base_enum (KeyError) */
+       DAN_MASK_E_UNSUPPORTED = 2,                   /* neither SNP (both alleles in "AaTtCcG"), delete nor insert: equal lengths (UnboundLocalError) */
+       DAN_MASK_E_SHAPE = 3,                         /* delete with ALT longer than one base / insert with REF longer than one base (assert) */
+       DAN_MASK_E_REF_MISMATCH = 4,                  /* window does not hold the record's reference bases (assert) */
+       DAN_MASK_E_WINDOW = 5 };                      /* allele runs past the window (ValueError) or no base at or before the centre */
+#define DAN_MASK_READ_LEN 201
+int dan_make_mask_vectors(const char* const* ref_alleles, const char* const* var_alleles, const uint8_t* references, int n,
+                          uint8_t* ref_masks, uint8_t* var_masks, int32_t* status);
+
 /* Test hook for the bit-exact integer/encoding work (dl4vc/model.py:450-627,719): writes the conv-1 input in the
  * reference's logical order (batch, Cin, num_reads, read_len) fp32, DEVICE pointer. */
 int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,

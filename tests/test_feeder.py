@@ -77,3 +77,25 @@ def test_native_vcf_info_formatting_matches_python():
     import pytest
     with pytest.raises(RuntimeError):
         format_vcf_info_native(np.full((1, 4), 1.5, np.float32))
+
+
+def test_mask_vector_decode_matches_reference_goldens():
+    """dan_make_mask_vectors (host code in the C-ABI library) against 600 records run through the REAL get_read_mask_vectors
+    (dl4vc/dataset.py:112-250; tests/golden/mask_vectors.npz from oracle/make_mask_goldens.py): SNPs, deletes with and without gap
+    columns, inserts (ALT clipped to 51 bases), rewinds past gap columns at the centre, and every record the reference raises on."""
+    import os
+    import pytest
+    from dl4vc_b200.feeder import make_mask_vectors
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mask_vectors.npz"))
+    xs, ys = [str(a) for a in g["ref_alleles"]], [str(a) for a in g["var_alleles"]]
+    rm, vm, st = make_mask_vectors(xs, ys, g["references"], strict=False)
+    ok = g["ok"].astype(bool)
+    assert np.array_equal(st == 0, ok), "the set of records the reference raises on differs"
+    assert np.array_equal(rm[ok], g["ref_masks"][ok]) and np.array_equal(vm[ok], g["var_masks"][ok])
+    assert not rm[~ok].any() and not vm[~ok].any()
+    assert ok.sum() > 400 and (~ok).sum() > 40
+    with pytest.raises(RuntimeError):
+        make_mask_vectors(xs, ys, g["references"], strict=True)
+    good = np.nonzero(ok)[0][:50]
+    rm2, vm2, st2 = make_mask_vectors([xs[i] for i in good], [ys[i] for i in good], g["references"][good])
+    assert not st2.any() and np.array_equal(rm2, g["ref_masks"][good])
