@@ -14,14 +14,15 @@ DAN_MAX_FC = 4
 NUM_HEAD_OUTPUTS = 27
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1
+FLAG_LAYERWISE = 1
 
 LIB_PATH = os.environ.get("DAN_B200_LIB") or os.path.join(os.path.dirname(os.path.abspath(__file__)), "libdan_b200.so")   # override: A/B builds during development
 
-# every symbol include/dan_b200.h declares (checked by tests/test_capi_symbols.py)
+# every symbol include/dan_b200.h declares (checked by tests/test_model_interface.py and __graft_entry__.build)
 EXPORTED_SYMBOLS = (
     "dan_last_error", "dan_version", "dan_model_create", "dan_model_destroy", "dan_model_load_weights",
     "dan_model_set_pass_candidates", "dan_workspace_bytes", "dan_forward", "dan_workspace_bytes_host",
-    "dan_forward_host", "dan_scores", "dan_format_vcf_info", "dan_make_mask_vectors", "dan_encode", "dan_debug_fc_input", "dan_last_launch_count",
+    "dan_forward_host", "dan_scores", "dan_format_vcf_info", "dan_make_mask_vectors", "dan_encode", "dan_encode_bf16", "dan_model_set_flags", "dan_debug_fc_input", "dan_last_launch_count",
     "dan_profile_enable", "dan_profile_read", "dan_profile_class_name",
 )
 PROF_NUM_CLASSES = 4
@@ -89,6 +90,8 @@ def load_library(path: str | None = None):
     lib.dan_forward.argtypes = fwd
     lib.dan_forward_host.argtypes = fwd
     lib.dan_encode.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.dan_encode_bf16.argtypes = [vp, vp, vp, vp, vp, vp, vp, i32, vp, vp]
+    lib.dan_model_set_flags.argtypes = [vp, i32]
     lib.dan_debug_fc_input.argtypes = [vp, i32, i32, vp, vp, vp]
     lib.dan_scores.argtypes = [vp, i32, vp, vp]
     lib.dan_format_vcf_info.argtypes = [vp, i32, vp, sz]

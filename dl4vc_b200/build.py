@@ -35,37 +35,42 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT) -> str:
+    """defines / out: development builds beside the product library (e.g. --prof: cycle counters in the conv-stack kernel,
+    loaded through DAN_B200_LIB)."""
+    if not force and not defines and not _stale():
         return OUT
     nvcc = nvcc_path()
     objs = []
-    build_dir = os.path.join(HERE, "build")
+    build_dir = os.path.join(HERE, "build" + ("_" + "_".join(defines).lower() if defines else ""))
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
         obj = os.path.join(build_dir, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, "-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [nvcc, *NVCC_FLAGS, *["-D" + d for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, obj, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     log = []
     for src, obj, p in procs:
-        out, _ = p.communicate()
-        log.append(out)
+        text, _ = p.communicate()
+        log.append(text)
         if p.returncode != 0:
-            sys.stderr.write(out)
+            sys.stderr.write(text)
             raise RuntimeError(f"nvcc failed on {src}")
         objs.append(obj)
     with open(os.path.join(build_dir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    cmd = [nvcc, "-shared", "-o", OUT, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcuda"]
+    cmd = [nvcc, "-shared", "-o", out, *objs, "-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcuda"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
-    return OUT
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--prof" in sys.argv:
+        print(build(force=True, verbose="-v" in sys.argv, defines=("DAN_STK_PROF",), out=os.path.join(HERE, "libdan_b200_prof.so")))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

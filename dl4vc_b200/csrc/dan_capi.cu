@@ -190,7 +190,9 @@ int dan_model_create(const dan_config* cfg, dan_model** out) {
   m->fcIn = (c.pool_combine_dimension > 0 ? c.pool_combine_dimension : m->pooled) + m->hwFeat;
   m->fcInPad = round_up_i(m->fcIn, 16);
   m->hidden = c.fc_sizes[c.num_fc - 1];
-  m->pass_candidates = 148;    // 148 candidates x 100 reads = 100 reads per CTA of the persistent stack kernel on a 148-SM B200: no tail imbalance
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, m->device);
+  m->pass_candidates = sms;    // one candidate per CTA of the persistent stack kernel (B200: 148 candidates x 100 reads = 100 reads per CTA, no tail imbalance)
   m->host_mu = new std::mutex();
   *out = m;
   return DAN_OK;
@@ -226,6 +228,12 @@ int dan_model_load_weights(dan_model* m, const dan_weights* w, void* stream) {
 int dan_model_set_pass_candidates(dan_model* m, int candidates) {
   if (!m || candidates < 1) { dan_set_error("pass_candidates must be >= 1"); return DAN_E_INVALID; }
   m->pass_candidates = candidates;
+  return DAN_OK;
+}
+
+int dan_model_set_flags(dan_model* m, int flags) {
+  if (!m || (flags & ~DAN_FLAG_LAYERWISE)) { dan_set_error("unknown flag bits %d", flags); return DAN_E_INVALID; }
+  m->flags = flags;
   return DAN_OK;
 }
 
@@ -354,6 +362,15 @@ int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, cons
   if (batch == 0) return DAN_OK;
   DevInputs in{reads, q_scores, strands, ref, ref_masks, var_masks};
   return dan_fp32_encode_reference_order(m, in, batch, x0_out, static_cast<cudaStream_t>(stream));
+}
+
+int dan_encode_bf16(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands, const uint8_t* ref,
+                    const uint8_t* ref_masks, const uint8_t* var_masks, int batch, float* x0_out, void* stream) {
+  int rc = check_forward_args(m, DAN_PRECISION_BF16, reads, q_scores, strands, ref, ref_masks, var_masks, batch, x0_out);
+  if (rc) return rc;
+  if (batch == 0) return DAN_OK;
+  DevInputs in{reads, q_scores, strands, ref, ref_masks, var_masks};
+  return dan_bf16_encode_reference_order(m, in, batch, x0_out, static_cast<cudaStream_t>(stream));
 }
 
 int dan_scores(const float* heads, int batch, float* scores_out, void* stream) {

@@ -81,6 +81,7 @@ struct dan_model {
   int fcIn, fcInPad;         // FC trunk input width
   int hidden;                // last FC width
   int pass_candidates;       // candidates per conv-stack pass
+  int flags;                 // DAN_FLAG_* (dan_model_set_flags)
   bool loaded;
   // ---- fp32 packed weights (device). GEMM weights are stored K-major: W[k][n], n contiguous. ----
   float* emb; float* pe;
@@ -126,6 +127,7 @@ size_t dan_bf16_workspace_bytes(const dan_model* m, int batch);
 int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_out, void* ws, size_t ws_bytes,
                      cudaStream_t st);
 int dan_bf16_debug_fc_input(dan_model* m, int batch, const void* ws, float* out, cudaStream_t st);
+int dan_bf16_encode_reference_order(dan_model* m, const DevInputs& in, int batch, float* x0_out, cudaStream_t st);
 int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st);
 void dan_bf16_free(dan_model* m);
 int dan_bf16_supported(const dan_model* m);

@@ -1,28 +1,37 @@
 // dan_stack.cuh — fused, persistent conv-stack kernel (bf16 tcgen05). Included by dan_bf16.cu.
 //
-// One launch runs a SEGMENT of consecutive conv layers (a maximal run without a read-axis pool-add in between:
-// PROD = layers 1-2, then layers 3-7; dl4vc/model.py:728-778) for every read of a pass. A read (201 positions x 128
-// channels, bf16) is loaded once into shared memory, goes through all layers of the segment IN PLACE and is written
-// back once; per-read activations between layers never touch HBM.
+// One launch runs a SEGMENT of consecutive conv layers (a maximal run without a read-axis pool-add in between: PROD = layers
+// 1-2, then layers 3-7; dl4vc/model.py:728-778) for every read of a pass. A read (201 positions x 128 channels, bf16) is
+// built (segment 1: embedding gather + positional / reference / q-score / strand / match-mask channels straight from the
+// loader's uint8 tiles, model.py:450-627) or loaded once into shared memory, goes through all layers of the segment IN PLACE,
+// and leaves the SM only as what the rest of the network consumes:
+//   * the bottleneck outputs T of every layer (A operand of the highway compression GEMM, model.py:774-776),
+//   * segment 1: the layer-2 output planes (re-read by segment 2) and their read-axis SUM (model.py:766-772),
+//   * last segment: the read-axis MAX and SUM of the final layer (model.py:824-826); the per-read activations of the final
+//     layer are never written.
+// The read-axis reductions are done by the TMA engine on the read's output planes while they are still in shared memory
+// (cp.reduce.async.bulk .max.bf16 / .add.noftz.bf16 into per-candidate accumulators in L2): max is exact; sums are kept per
+// (block of 20 reads, slot) so that every accumulator sees at most 10 bf16 additions in a fixed order before the finishing
+// kernel adds the groups in fp32 (deterministic, 7e-4 rms of the sum). The first read of a group STORES, so nothing is zeroed.
 //
 // Orientation ("D^T"): for one read and one layer the tensor core computes
 //       D[cout 0..127][position 0..207] = sum_tap  W_tap[cout][cin] * X[position + (tap-1)*dil][cin]
 // i.e. M = 128 output channels (A operand = weights, streamed from L2 through a shared-memory ring), N = 208 positions
 // (B operand = the read's activation buffer; a dilated tap is a row offset of the descriptor start address, the zero
 // rows around the read implement Conv2d's zero padding, model.py:214-229), accumulator = 208 TMEM columns.
-// 201 -> 208 padding costs 3.4 % (a positions-as-M tiling would cost 21 %). The epilogue reads the accumulator in the
-// mma C-fragment layout (tcgen05.ld 16x256b), applies +bias -> ReLU -> BatchNorm with per-thread channel constants
-// (model.py:749-751) and writes bf16 back into the activation buffer with stmatrix.trans, which performs the
-// [channel][position] -> [position][channel] transpose for free.
-// Residual layers (model.py:753-761): the same epilogue pre-loads the accumulator with x + b_res (tcgen05.st), a
-// second MMA pass accumulates W_res * y on top, and a second epilogue writes the layer output.
-// Highway bottleneck (model.py:773-774): positions-as-M orientation (D3[position][32]) so that N = 32 is legal; its
-// epilogue writes relu(.)+bias to the T matrix consumed by the compression GEMM.
+// The epilogue reads the accumulator in the mma C-fragment layout (tcgen05.ld 16x256b), applies +bias -> ReLU -> BatchNorm
+// (model.py:749-751) and writes bf16 back into the activation buffer with stmatrix.trans (free transpose).
+// Residual layers (model.py:753-761): the epilogue pre-loads the accumulator with x + b_res (tcgen05.st), a second MMA pass
+// accumulates W_res * y on top, and a second epilogue writes the layer output.
+// Highway bottleneck (model.py:773-774): positions-as-M orientation (D3[position][32]); it reads the same buffer state as the
+// NEXT layer's conv, so the two are issued as ONE op — bottleneck MMAs first, into a small accumulator of their own (TMEM
+// columns 224..255 and 480..511, shared by the two slots under a small lock), then the conv MMAs: the bottleneck
+// epilogue (relu, bf16, T store) runs under the conv MMAs instead of forming an op + epilogue round trip of its own.
 //
-// Per CTA: two independent read pipelines ("slots": own accumulator, own epilogue warpgroup, own weight ring) that
-// the single MMA-issuing thread multiplexes at weight-stage granularity, so one slot's epilogue runs under the other
-// slot's MMAs; three activation buffers rotate so that the next read's load and the previous read's store overlap
-// with compute.
+// Per CTA: two independent read pipelines ("slots": own main accumulator, own epilogue warps, own issuer warp). ONE weight
+// ring (14 x 8 KB stages) feeds both: slot 1 runs one op behind slot 0 and every stage is consumed twice before it is
+// refilled. Work is handed out in blocks of 20 reads of one candidate; a block with an odd number of reads is completed by
+// a phantom read (same op sequence, no global side effects), so both slots always run identical op sequences.
 #pragma once
 
 namespace {
@@ -35,13 +44,19 @@ constexpr int kStkRB = kStkLead + kStkN + 2;   // rows per channel-chunk plane o
 constexpr int kStkPlane = kStkRB * 16;         // bytes per plane (3392)
 constexpr int kStkBuf = kKC * kStkPlane;       // bytes per read buffer (54272)
 constexpr int kStkStageBytes = 8192;   // weight-ring stage = two k-step blocks of 4 KB
-constexpr int kStkStages = 14;         // stages of the weight ring shared by the two slots (>= largest op (12) + prefetch)
+constexpr int kStkStages = 7;          // stages of EACH slot's private weight ring (prefetch depth; a slot's ops never wait for the other slot's consumption)
 constexpr int kStkMaxSeg = 8;          // layers per segment
 constexpr int kStkRegsIssue = 56, kStkRegsEpi = 104;   // setmaxnreg redistributes the launch allocation (640 x 96): 128 x 56 + 512 x 104 = 60416 <= 61440
 constexpr int kStkBmapChunk = 64;       // uint4 per (role, 16-position chunk) of the pool bias map: 32 lanes x 2 (bmap_pack_kernel, dan_bf16.cu)
 constexpr int kStkBmapPerCand = 8 * 7 * kStkBmapChunk;   // uint4 per candidate: 8 roles (position half, lane quadrant) x 7 chunks
-constexpr int kStkSmemHeader = 3072;   // barriers, TMEM pointer, bottleneck biases of the segment
-constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + kStkStages * kStkStageBytes;
+constexpr int kStkBott = 32;            // bottleneck width the fused kernel is built for (PROD; other widths take the layer-wise path)
+constexpr int kStkAccStride = 256;      // TMEM columns between the two slots' main accumulators (208 used)
+constexpr int kStkBottCol0 = 224, kStkBottCol1 = 480;   // shared bottleneck accumulator: position tile 0 / 1 (32 columns each) in the gaps behind the main accumulators
+constexpr int kStkBlockReads = 20;      // work unit: consecutive reads of one candidate = one sum group per slot
+constexpr int kStkSmemHeader = 3072;    // barriers, TMEM pointer, bottleneck biases of the segment
+constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + 2 * kStkStages * kStkStageBytes;
+
+enum { kStkInPlanes = 0, kStkInEncode = 1 };
 
 struct StackLayer {
   const uint8_t* wstream;   // conv k-step blocks (tap-major) | residual blocks | bottleneck blocks, contiguous
@@ -51,77 +66,166 @@ struct StackLayer {
   uint4* tout;              // T[read][c/8][p][c%8] (bf16) of this layer: row-major A operand (K = (c/8, p, c%8)) of the compression GEMM
   int conv_blocks;          // 3 * kc_in / 2
   int kc_in;                // 16-byte pieces per input row (CinPad/8 for layer 1, else 16)
-  int dil, residual, highway;
+  int dil, residual;
 };
 
 struct StackParams {
-  const uint4* in; long in_kstride;     // chunk-major input rows (dan_bf16.cu), in_kc planes
-  uint4* out; long out_kstride;         // chunk-major output rows, 16 planes
-  long t_reads_stride;
-  int num_reads, P, pitch, bott, num_layers;
-  const float* pool; int reads_per_cand;   // optional read-mean of the previous segment, fp32 [candidate][c/8][p][8]: added to every read on load (model.py:742)
-  const uint4* bmap;                   // optional pool bias map conv(pool) + bias of the segment's first layer (replaces `pool`), [candidate][kStkBmapPerCand]
-  unsigned long long* prof;            // optional [grid][16] cycle counters (development aid), or null
-  uint2* trace; int trace_cap;         // development: event trace of CTA 0 (id, clock), trace[0].x = count
-  int debug;                           // development: bit 0 = skip the MMAs, bit 1 = skip epilogue math/stores
+  int in_mode;                          // kStkInPlanes: chunk-major rows from `in`; kStkInEncode: built from the uint8 pileup tiles
+  const uint4* in; long in_kstride;     // chunk-major input rows (dan_bf16.cu), kc_in planes
+  DevInputs bytes; long cand0;          // encode mode: loader tensors of the batch and the first candidate of this pass
+  const uint4* enc_tab;                 // encode mode: bf16(E[tok] + pe[p]) as [P][10 tokens][3 pieces] (enc_table_kernel)
+  uint4* out; long out_kstride;         // optional: chunk-major output rows of the segment, 16 planes
+  uint4* sums; int groups_per_cand;     // optional: read-axis sum groups [candidate][group][c/8][p] pieces (bf16)
+  uint4* maxv; long max_stride;         // optional: read-axis max [candidate * max_stride + (c/8) * P + p] pieces (bf16), pre-set to -inf
+  const uint4* bmap;                    // optional pool bias map conv(pool) + bias of the segment's first layer, [candidate][kStkBmapPerCand]
+  int cands, R, P, pitch, highway, num_layers;
+  int lag_ops;                          // slot 1 starts its op n once slot 0 has issued op n + lag_ops - 1 (>= 1): how far the two slots run out of phase
+#ifdef DAN_STK_PROF
+  unsigned long long* prof;             // development build: [grid][48] cycle counters
+#endif
   StackLayer layer[kStkMaxSeg];
 };
 
 struct StackSmem {
-  uint64_t w_full[kStkStages], w_empty[kStkStages];
-  uint64_t acc_full[2], act_ready[2], in_full[2];
+  uint64_t w_full[2][kStkStages], w_empty[2][kStkStages];
+  uint64_t acc_full[2], act_ready[2], in_full[2], bott_full[2];
+  uint32_t bott_busy, bott_drained;    // the shared bottleneck accumulator: taken by an issuer (CAS 0 -> 1), given back by the last of the 256 epilogue threads that read it out
   uint32_t tmem_base;
   uint32_t issued_ops;                 // ops fully issued by slot 0's issuer (slot 1 runs one op behind, see the issuer)
-  float bbias[kStkMaxSeg][64];
+  float bbias[kStkMaxSeg][kStkBott];
 };
 static_assert(sizeof(StackSmem) <= kStkSmemHeader, "header too small");
+
+// Walks the read pairs of a CTA's share of the pass: blocks of kStkBlockReads reads of one candidate, two reads (slot 0, slot 1) per
+// step. Carried incrementally (no division on the per-read path): candidate, block within the candidate, pair within the block.
+struct StkIter {
+  int cand, bic, pr, left;      // left = blocks of this CTA still to do (including the current one)
+  __device__ static int bpc(int R) { return (R + kStkBlockReads - 1) / kStkBlockReads; }
+  __device__ void init(int cands, int R) {
+    const int total = cands * bpc(R), per = total / (int)gridDim.x, rem = total % (int)gridDim.x;
+    const int first = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
+    left = per + ((int)blockIdx.x < rem ? 1 : 0);
+    cand = first / bpc(R); bic = first - cand * bpc(R); pr = 0;
+  }
+  __device__ bool done() const { return left <= 0; }
+  __device__ int nr(int R) const { return min(kStkBlockReads, R - bic * kStkBlockReads); }
+  __device__ void next(int R) {
+    if (++pr == (nr(R) + 1) >> 1) {
+      pr = 0; --left;
+      if (++bic == bpc(R)) { bic = 0; ++cand; }
+    }
+  }
+  __device__ bool valid(int R, int s) const { return 2 * pr + s < nr(R); }       // slot 1 of the last pair of an odd block is a phantom
+  __device__ int read_in_cand(int s) const { return bic * kStkBlockReads + 2 * pr + s; }
+  __device__ int group(int s) const { return 2 * bic + s; }
+};
+__device__ inline int stk_total_pairs(int cands, int R) {
+  StkIter it;
+  it.init(cands, R);
+  int n = 0;
+  for (; it.left > 0; --it.left) {
+    n += (it.nr(R) + 1) >> 1;
+    if (++it.bic == StkIter::bpc(R)) it.bic = 0;
+  }
+  return n;
+}
+
+__device__ __forceinline__ void bulk_reduce_max_bf16(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.max.bf16 [%0], [%1], %2;" ::"l"(gmem_dst), "r"(ptx::smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_bf16(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.noftz.bf16 [%0], [%1], %2;" ::"l"(gmem_dst), "r"(ptx::smem_u32(smem_src)), "r"(bytes) : "memory");
+}
+// barrier + AND-reduction of a predicate over the `threads` threads that use named barrier `id` (1 or 2)
+__device__ __forceinline__ bool named_bar_and(uint32_t id, uint32_t threads, bool pred) {
+  uint32_t r;
+  if (id == 1) asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %2, 0;\n\tbarrier.cta.red.and.pred p, 1, %1, q;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"(threads), "r"((uint32_t)pred) : "memory");
+  else asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 q, %2, 0;\n\tbarrier.cta.red.and.pred p, 2, %1, q;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(r) : "r"(threads), "r"((uint32_t)pred) : "memory");
+  return r != 0;
+}
 
 }  // namespace
 #include "dan_stack_epi.cuh"
 namespace {
 
+#ifdef DAN_STK_PROF
+#define STK_PROF_DECL long long prof_t0 = clock64(), prof_acc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_begin = prof_t0
+#define STK_PROF(i) do { const long long prof_t1 = clock64(); prof_acc[i] += prof_t1 - prof_t0; prof_t0 = prof_t1; } while (0)
+#define STK_PROF_FLUSH(cond, base) do { if (cond) { for (int i_ = 0; i_ < 14; ++i_) p.prof[blockIdx.x * 64 + (base) + i_] = prof_acc[i_]; } } while (0)
+#else
+#define STK_PROF_DECL
+#define STK_PROF(i)
+#define STK_PROF_FLUSH(cond, base)
+#endif
+
 // descriptor words: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14  (tcgen05_ptx.cuh make_smem_desc)
 __device__ __forceinline__ uint64_t stk_desc(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
-// role = 0,1 issuer of slot 0,1; 2,3 epilogue of slot 0,1: each role logs into its own quarter of the buffer (no atomics)
-__device__ __forceinline__ void stk_trace(const StackParams& p, int role, int& n, uint32_t id) {
-  if (p.trace && blockIdx.x == 0) {
-    const int cap = p.trace_cap / 4;
-    if (n < cap) p.trace[role * cap + n++] = make_uint2(id, (uint32_t)clock64());
+// ---- pileup encoder of one read (model.py:450-627,719), run by the 256 epilogue threads of a slot: thread t owns position t.
+// Bytes of the read (token, q-score, strand) are requested early (stk_enc_fetch) and turned into the six 8-channel planes of the
+// conv-1 input later (stk_enc_write):  0-19 E[tok]+pe | 20-39 E[ref]+pe | 40 q*0.01 | 41 strand*0.5 | 42 ref-match | 43 var-match |
+// 44 var-length (from the REF mask, model.py:579,584) | 45-47 zero. Integer work (agreement of the read with the ref / var
+// proposal over all 201 positions) is an AND-reduction over the slot's threads; the float channels come from a bf16 table of
+// E[tok] + pe[p] built once per weight load, so every value is bf16_rn of the reference's fp32 value.
+typedef uint32_t StkEncBytes;      // token | q-score << 8 | strand << 16
+
+__device__ __forceinline__ StkEncBytes stk_enc_fetch(const StackParams& p, long cand, int r, int pos) {
+  StkEncBytes b = 0u;
+  if (pos < p.P) {
+    const long off = (cand * p.P + pos) * p.R + r;
+    b = (uint32_t)__ldg(p.bytes.reads + off) | (uint32_t)__ldg(p.bytes.q + off) << 8 | (uint32_t)__ldg(p.bytes.strands + off) << 16;
+  }
+  return b;
+}
+
+__device__ __forceinline__ void stk_enc_write(const StackParams& p, long cand, int pos, int s, StkEncBytes eb, uint8_t* buf) {
+  const uint32_t tok = eb & 0xFFu, qv = (eb >> 8) & 0xFFu, sv = eb >> 16;
+  uint32_t refp = 0, rmk = 0, vmk = 0;
+  if (pos < p.P) { refp = __ldg(p.bytes.ref + cand * p.P + pos); rmk = __ldg(p.bytes.ref_masks + cand * p.P + pos); vmk = __ldg(p.bytes.var_masks + cand * p.P + pos); }
+  const bool agreeR = named_bar_and(1 + s, kStkEpiThreads, rmk == 0 || tok == rmk);       // model.py:592-593
+  const bool agreeV = named_bar_and(1 + s, kStkEpiThreads, vmk == 0 || tok == vmk);       // model.py:607-608
+  if (pos < p.P) {
+    const uint4* tr = p.enc_tab + ((long)pos * DAN_VOCAB + min(tok, (uint32_t)DAN_VOCAB - 1)) * 3;
+    const uint4* tf = p.enc_tab + ((long)pos * DAN_VOCAB + min(refp, (uint32_t)DAN_VOCAB - 1)) * 3;
+    const uint4 r0 = __ldg(tr), r1 = __ldg(tr + 1), r2 = __ldg(tr + 2), a0 = __ldg(tf), a1 = __ldg(tf + 1), a2 = __ldg(tf + 2);
+    const float m0 = (rmk != 0 && agreeR) ? 1.f : 0.f, m1 = (vmk != 0 && agreeV) ? 1.f : 0.f, m2 = rmk != 0 ? 1.f : 0.f;
+    uint4* row = reinterpret_cast<uint4*>(buf + (size_t)(kStkLead + pos) * 16);
+    constexpr int kPl = kStkPlane / 16;
+    row[0] = r0; row[kPl] = r1;
+    row[2 * kPl] = make_uint4(r2.x, r2.y, a0.x, a0.y);
+    row[3 * kPl] = make_uint4(a0.z, a0.w, a1.x, a1.y);
+    row[4 * kPl] = make_uint4(a1.z, a1.w, a2.x, a2.y);
+    row[5 * kPl] = make_uint4(pack_bf16x2((float)qv * 0.01f, (float)sv * 0.5f), pack_bf16x2(m0, m1), pack_bf16x2(m2, 0.f), 0u);   // model.py:24,16
   }
 }
 
-// kDev: 0 = production, 1 = honours the debug skip flags only, 2 = + cycle counters, 3 = + event trace instead (development builds)
-template <int kDev>
 __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_constant__ StackParams p) {
-  const bool prof_on = kDev == 2 && p.prof != nullptr, trace_on = kDev == 3 && p.trace != nullptr;
   extern __shared__ __align__(1024) uint8_t smem[];
   StackSmem* sm = reinterpret_cast<StackSmem*>(smem);
   uint8_t* bufs = smem + kStkSmemHeader;
   uint8_t* rings = bufs + 2 * (size_t)kStkBuf;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  const int per = p.num_reads / (int)gridDim.x, rem = p.num_reads % (int)gridDim.x;
-  const int r_begin = (int)blockIdx.x * per + min((int)blockIdx.x, rem);
-  const int n_reads = per + ((int)blockIdx.x < rem ? 1 : 0);
-  const uint32_t plane_bytes_in = (uint32_t)p.P * 16;
+  const uint32_t plane_bytes = (uint32_t)p.P * 16;
   const int in_kc = p.layer[0].kc_in;
+  const int n_layers = p.num_layers;
+  const bool highway = p.highway != 0;
 
   {  // zero rows / planes must read as 0 until an epilogue or a load writes them
     uint4* z = reinterpret_cast<uint4*>(bufs);
     for (int i = threadIdx.x; i < 2 * kStkBuf / 16; i += kStkThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < kStkStages; ++i) { mbar_init(&sm->w_full[i], 1); mbar_init(&sm->w_empty[i], 2); }   // both slots release a stage
+    for (int i = 0; i < 2 * kStkStages; ++i) { mbar_init(&sm->w_full[0][i], 1); mbar_init(&sm->w_empty[0][i], 1); }
     sm->issued_ops = 0;
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], kStkEpiThreads); mbar_init(&sm->in_full[s], 1);
+      mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], kStkEpiThreads); mbar_init(&sm->in_full[s], 1); mbar_init(&sm->bott_full[s], 1);
     }
+    sm->bott_busy = 0; sm->bott_drained = 0;
     fence_mbar_init();
   }
-  for (int i = threadIdx.x; i < p.num_layers * 64; i += kStkThreads) {
-    const int l = i >> 6, c = i & 63;
-    sm->bbias[l][c] = (p.layer[l].highway && c < p.bott) ? p.layer[l].bbias[c] : 0.f;
+  for (int i = threadIdx.x; i < n_layers * kStkBott; i += kStkThreads) {
+    const int l = i / kStkBott, c = i - l * kStkBott;
+    sm->bbias[l][c] = highway ? p.layer[l].bbias[c] : 0.f;
   }
   fence_proxy_async_smem();
   if (warp == 18) tmem_alloc<512>(&sm->tmem_base);
@@ -130,104 +234,81 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
   tc_fence_after();
   const uint32_t tmem_base = sm->tmem_base;
 
-  // global -> shared load of local read i into its slot's buffer, spread over the slot's 8 epilogue warps: lane 0 of warp wl moves
-  // chunk planes 2*wl and 2*wl + 1 and prefetches the same planes of the slot's next read into L2. A bulk-copy instruction costs its
-  // issuing thread ~170 cycles (and divergent lanes of one warp are serialised), so one thread issuing 2 x in_kc of them kept the
-  // slot waiting 5-6 k cycles at every read boundary. The barrier must be armed (arm_read) before any of the copies can complete.
-  auto arm_read = [&](int i) { mbar_expect_tx(&sm->in_full[i & 1], plane_bytes_in * in_kc); };
-  auto load_read_planes = [&](int i, int wl) {
-    const int s = i & 1;
-    const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
-    uint8_t* dst = bufs + (size_t)s * kStkBuf + kStkLead * 16;
-    const uint64_t once = l2_policy_evict_first();          // activations stream through: read once, written once
-    for (int kc = 2 * wl; kc < 2 * wl + 2 && kc < in_kc; ++kc)
-      bulk_g2s_hint(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes_in, &sm->in_full[s], once);
-  };
-  auto prefetch_read_planes = [&](int i, int wl) {           // read i into L2, so that its load (on the slot's critical path) is an L2 hit
-    const uint4* src = p.in + kLead + (long)(r_begin + i) * p.pitch;
-    for (int kc = 2 * wl; kc < 2 * wl + 2 && kc < in_kc; ++kc) bulk_prefetch_l2(src + kc * p.in_kstride, plane_bytes_in);
-  };
+  const int n_pairs = stk_total_pairs(p.cands, p.R);
 
   // register budget: the producer / issuer warpgroup (warps 16-19) hands registers to the four epilogue warpgroups
   if (warp >= 16) {
-#ifndef DAN_STK_NO_SETMAXNREG
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kStkRegsIssue));
-#endif
   if (warp == 16 || warp == 17) {
-    // ===================== weight producer: ONE stream for both slots. The two reads of a pair go through the same op
-    // sequence one op apart (see the issuers), so every stage is consumed twice before it is refilled: the L2 -> SMEM
-    // weight traffic (the binding resource of this kernel when each slot streamed its own copy) is halved. =========
-    // Two producer threads (lane 0 of warps 16 and 17) take alternate stages of the stream: one thread needs ~300 cycles per
-    // stage (empty-barrier probe + expect_tx + copy issue), which is close to the rate at which the tensor pipe drains a stage.
-    if (lane == 0 && !(kDev != 0 && (p.debug & 16))) {
-      const uint32_t mine = (uint32_t)(warp - 16);
-      const uint64_t keep = l2_policy_evict_last();          // the weight images are re-read by every CTA for every pair of reads
-      uint32_t idx = 0, par = 1, seq = 0;     // first pass over the ring: the "empty" phase counts as complete
+    // ===================== weight producers: lane 0 of warp 16 + s streams the layer weights of slot s's reads into that slot's ring
+    // (~300 cycles per stage: empty-barrier probe + expect_tx + copy issue; the tensor pipe drains a stage in ~210).
+    if (lane == 0) {
+      const int s = warp - 16;
+      uint64_t* const wfull = &sm->w_full[s][0];
+      uint64_t* const wempty = &sm->w_empty[s][0];
+      uint8_t* const ring = rings + (size_t)s * kStkStages * kStkStageBytes;
+      const uint64_t keep = l2_policy_evict_last();          // the weight images are re-read by every CTA for every read
+      uint32_t idx = 0, par = 1;              // first pass over the ring: the "empty" phase counts as complete
       auto emit = [&](const uint8_t* src, uint32_t bytes) {
         for (uint32_t off = 0; off < bytes; off += kStkStageBytes) {
-          if ((seq++ & 1u) == mine) {
-            const uint32_t n = min((uint32_t)kStkStageBytes, bytes - off);
-            mbar_wait(&sm->w_empty[idx], par);
-            mbar_expect_tx(&sm->w_full[idx], n);
-            bulk_g2s_hint(rings + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[idx], keep);
-          }
+          const uint32_t n = min((uint32_t)kStkStageBytes, bytes - off);
+          mbar_wait(&wempty[idx], par);
+          mbar_expect_tx(&wfull[idx], n);
+          bulk_g2s_hint(ring + (size_t)idx * kStkStageBytes, src + off, n, &wfull[idx], keep);
           if (++idx == kStkStages) { idx = 0; par ^= 1; }
         }
       };
-      for (int i = 0; i < n_reads; i += 2) {
-        for (int l = 0; l < p.num_layers; ++l) {
+      for (int pr = 0; pr < n_pairs; ++pr) {
+        for (int l = 0; l < n_layers; ++l) {
           const StackLayer& L = p.layer[l];
           const uint32_t conv_bytes = (uint32_t)L.conv_blocks * 4096u;
-          const uint8_t* w = L.wstream + (size_t)(blockIdx.x % kWeightReplicas) * L.wreplica_stride;
+          const uint8_t* w = L.wstream + (size_t)((2 * blockIdx.x + s) % kWeightReplicas) * L.wreplica_stride;
           emit(w, conv_bytes);
           if (L.residual) emit(w + conv_bytes, kKC / 2 * 4096u);
-          if (L.highway) emit(w + conv_bytes + (L.residual ? kKC / 2 * 4096u : 0u), (uint32_t)kKC * p.bott * 16u);
+          if (highway) emit(w + conv_bytes + (L.residual ? kKC / 2 * 4096u : 0u), (uint32_t)kKC * kStkBott * 16u);
         }
       }
     }
   } else {
-    // ===================== MMA issuer of slot s. The whole warp runs the (blocking, strictly sequential) op schedule of
-    // its slot — warp-uniform control flow keeps descriptors in uniform registers — and one elected lane issues the
-    // tcgen05 instructions. The two slots' issuers are independent warps: the tensor pipe interleaves their MMA
-    // streams, so one slot's epilogue runs under the other slot's MMAs without any software multiplexing. A single
-    // warp retires one dependent instruction every ~4 cycles, so the loops below are kept to a few instructions
-    // per MMA (descriptor words are advanced by constants). =========================================================
+    // ===================== MMA issuer of slot s. The whole warp runs the (blocking, strictly sequential) op schedule of its slot —
+    // warp-uniform control flow keeps descriptors in uniform registers — and one elected lane issues the tcgen05 instructions. The
+    // two slots' issuers are independent warps: the tensor pipe interleaves their MMA streams, so one slot's epilogue runs under the
+    // other slot's MMAs. Op sequence of a read:  conv 1 | [bott l-1 + conv l] (| residual l) ... | bott L.
     const int s = warp - 18;
     const uint32_t idesc_main = make_idesc_bf16(128, kStkN);
-    const uint32_t idesc_bott = make_idesc_bf16(128, p.bott);
+    const uint32_t idesc_bott = make_idesc_bf16(128, kStkBott);
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
-    const uint32_t a_lbo_w = (2048u >> 4) << 16, b_lbo_x = ((uint32_t)kStkPlane >> 4) << 16, b_lbo_bott = (((uint32_t)p.bott * 16u) >> 4) << 16;
-    const int bott_per_stage = kStkStageBytes / (p.bott * 32);
-    const uint32_t ring_lo = smem_u32(rings) >> 4;
-    uint64_t* const wfull = &sm->w_full[0];
-    uint64_t* const wempty = &sm->w_empty[0];
+    const uint32_t a_lbo_w = (2048u >> 4) << 16, b_lbo_x = ((uint32_t)kStkPlane >> 4) << 16, b_lbo_bott = (((uint32_t)kStkBott * 16u) >> 4) << 16;
+    constexpr int kBottPerStage = kStkStageBytes / (kStkBott * 32);      // k-steps of bottleneck weights per ring stage (8 = all of them)
+    const uint32_t ring_lo = smem_u32(rings + (size_t)s * kStkStages * kStkStageBytes) >> 4;
+    uint64_t* const wfull = &sm->w_full[s][0];
+    uint64_t* const wempty = &sm->w_empty[s][0];
     volatile uint32_t* const issued = &sm->issued_ops;
     uint32_t gops = 0;                                                                            // ops started by this issuer
-    int tr_n = 0;
-    const uint32_t d_main = tmem_base + (uint32_t)s * 256u;
+    uint32_t total_ops = 0;
+    for (int l = 0; l < n_layers; ++l) total_ops += 1u + (p.layer[l].residual ? 1u : 0u);
+    total_ops = (total_ops + (highway ? 1u : 0u)) * (uint32_t)n_pairs;                           // ops of one slot over the whole launch
+    const uint32_t d_main = tmem_base + (uint32_t)s * kStkAccStride, d_bott0 = tmem_base + kStkBottCol0, d_bott1 = tmem_base + kStkBottCol1;
     const uint32_t x_lo = (smem_u32(bufs) >> 4) + (uint32_t)s * (kStkBuf >> 4) + kStkLead;       // centre row of chunk plane 0
     constexpr uint32_t kStep = 2 * (kStkPlane >> 4);                                              // one k-step = two chunk planes
-    uint32_t wi = 0, wp = 0, opc = 0;
-    const long long t_begin = clock64();
-    long long t_dep = 0, t_wfull = 0;
-    const bool do_mma = kDev == 0 || !(p.debug & 1);
-    const bool no_w = kDev != 0 && (p.debug & 16);     // development: weights are not streamed (garbage operands, timing only)
+    uint32_t wi = 0, wp = 0, opc = 0;      // ring position / parity, hand-overs awaited
     // The full-barrier probe of an op's first stage(s) is issued BEFORE the op's dependencies are awaited (prewait*): a probe costs
     // ~190 cycles even when the phase is complete, and there it would sit between the epilogue's hand-over and the op's first MMA.
     bool prewaited = false;
+    STK_PROF_DECL;
     auto wait_w = [&]() {
       if (prewaited) { prewaited = false; return; }
-      if (no_w) return;
-      if (prof_on) { const long long c0 = clock64(); mbar_wait(&wfull[wi], wp); t_wfull += clock64() - c0; }
-      else mbar_wait(&wfull[wi], wp);
+      STK_PROF(0);
+      mbar_wait(&wfull[wi], wp);
       tc_fence_after();
+      STK_PROF(1);
     };
     auto wait_w2 = [&](uint32_t wi1, uint32_t wp1) {
       if (prewaited) { prewaited = false; return; }
-      if (no_w) return;
-      if (prof_on) { const long long c0 = clock64(); mbar_wait2(&wfull[wi], wp, &wfull[wi1], wp1); t_wfull += clock64() - c0; }
-      else mbar_wait2(&wfull[wi], wp, &wfull[wi1], wp1);
+      STK_PROF(0);
+      mbar_wait2(&wfull[wi], wp, &wfull[wi1], wp1);
       tc_fence_after();
+      STK_PROF(1);
     };
     auto prewait1 = [&]() { wait_w(); prewaited = true; };
     auto prewait2 = [&]() {
@@ -236,56 +317,75 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       prewaited = true;
     };
     auto adv2 = [&](uint32_t wi1, uint32_t wp1) { wi = wi1 + 1; wp = wp1; if (wi == kStkStages) { wi = 0; wp ^= 1; } };
-    auto wait_dep = [&](bool first_of_read, int k) {
-      long long c0 = 0; if (prof_on) c0 = clock64();
+    auto wait_dep = [&](bool first_of_read, uint32_t k) {
       // slot 1 starts op n only after slot 0 has issued all of its op n: the tensor pipe then runs slot 1's MMAs under slot 0's
       // epilogue (and vice versa) instead of both slots computing and then both draining, and the lag between the two
-      // consumers of the shared weight ring stays within one op (<= 12 of the 14 stages).
+      // consumers of the shared weight ring stays within one op (<= 13 of the 14 stages).
       // (polled with a short sleep: a tight shared-memory spin would take issue slots from the epilogue warps of this warp's scheduler)
-      if (s == 1 && !(p.debug & 8)) { uint32_t spins = 0; while (*issued <= gops) { __nanosleep(32); if (++spins > (1u << 24)) __trap(); } }
+      STK_PROF(0);
+      if (s == 1) { const uint32_t need = min(gops + (uint32_t)p.lag_ops, total_ops); uint32_t spins = 0; while (*issued < need) { __nanosleep(32); if (++spins > (1u << 24)) __trap(); } }
       ++gops;
+      STK_PROF(2);
       mbar_wait(&sm->act_ready[s], opc & 1);
-      if (first_of_read) mbar_wait(&sm->in_full[s], (uint32_t)k & 1);
-      tc_fence_after();
-      if (prof_on) t_dep += clock64() - c0;
-      if (trace_on && lane == 0) stk_trace(p, s, tr_n, (uint32_t)s << 28 | 1u << 24 | (gops & 0xFFFFu));
-    };
-    auto op_done = [&]() {
-      if (elect_one()) {
-        umma_commit(&sm->acc_full[s]);
-        if (s == 0) { __threadfence_block(); *issued = gops; }
-      }
-      __syncwarp();
-      if (trace_on && lane == 0) stk_trace(p, s, tr_n, (uint32_t)s << 28 | 2u << 24 | (gops & 0xFFFFu));
       ++opc;
+      STK_PROF(3);
+      if (first_of_read && p.in_mode == kStkInPlanes) mbar_wait(&sm->in_full[s], k & 1);
+      tc_fence_after();
+      STK_PROF(4);
+    };
+    auto mark_issued = [&]() {
+      if (s == 0 && elect_one()) { __threadfence_block(); *issued = gops; }
+      __syncwarp();
+    };
+    auto commit_acc = [&]() {
+      if (elect_one()) umma_commit(&sm->acc_full[s]);
+      __syncwarp();
     };
     auto stage_done = [&]() {
-      if (!no_w && elect_one()) umma_commit(&wempty[wi]);
+      if (elect_one()) umma_commit(&wempty[wi]);
       __syncwarp();
       if (++wi == kStkStages) { wi = 0; wp ^= 1; }
     };
-    for (int i = s, k = 0; i < n_reads + (n_reads & 1); i += 2, ++k) {
-      if (i >= n_reads) {
-        // odd tail: slot 1 has no read in the last pair but must still release the stages streamed for slot 0's read
-        for (int l = 0; l < p.num_layers; ++l) {
-          const StackLayer& L = p.layer[l];
-          const int stages = (L.conv_blocks + 1) / 2 + (L.residual ? kKC / 4 : 0) + (L.highway ? p.bott / 32 : 0);
-          for (int st = 0; st < stages && !no_w; ++st) {
-            mbar_wait(&wfull[wi], wp);
-            if (elect_one()) mbar_arrive(&wempty[wi]);
-            __syncwarp();
-            if (++wi == kStkStages) { wi = 0; wp ^= 1; }
+    // bottleneck 1x1 of the layer whose output sits in the buffer, positions-as-M orientation: A = activation rows (two 128-row tiles),
+    // B = weights; accumulator = the shared columns, free once the other slot's epilogue has drained its previous use
+    auto issue_bott = [&]() {
+      STK_PROF(0);
+      if (lane == 0) { uint32_t spins = 0; while (atomicCAS(&sm->bott_busy, 0u, 1u) != 0u) { __nanosleep(32); if (++spins > (1u << 24)) __trap(); } }
+      __syncwarp();
+      tc_fence_after();
+      STK_PROF(5);
+      uint32_t xa_lo = x_lo | b_lbo_x;
+      for (int blk = 0; blk < kKC / 2; blk += kBottPerStage) {
+        wait_w();
+        const uint32_t w_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | b_lbo_bott;
+        if (elect_one()) {
+          uint32_t xa = xa_lo, wl = w_lo;
+#pragma unroll
+          for (int u = 0; u < kBottPerStage; ++u) {
+            umma_bf16(d_bott0, stk_desc(xa, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
+            umma_bf16(d_bott1, stk_desc(xa + 128u, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
+            xa += kStep;
+            wl += (uint32_t)kStkBott * 2u;
           }
+          umma_commit(&wempty[wi]);
         }
-        break;
+        __syncwarp();
+        xa_lo += (uint32_t)kBottPerStage * kStep;
+        if (++wi == kStkStages) { wi = 0; wp ^= 1; }
       }
-      for (int l = 0; l < p.num_layers; ++l) {
+      if (elect_one()) umma_commit(&sm->bott_full[s]);
+      __syncwarp();
+    };
+    for (int pr = 0; pr < n_pairs; ++pr) {
+      for (int l = 0; l < n_layers; ++l) {
         const StackLayer& L = p.layer[l];
-        const int residual = L.residual, highway = L.highway, ksteps = L.kc_in / 2, total = L.conv_blocks;
+        const int ksteps = L.kc_in / 2, total = L.conv_blocks;
         const uint32_t dil = (uint32_t)L.dil;
-        // ---- conv: D[cout][pos] = sum over taps and input-channel k-steps ----
-        if ((ksteps & 3) == 0) prewait2(); else prewait1();
-        wait_dep(l == 0, k);
+        const bool with_bott = highway && l > 0;
+        // ---- [bottleneck of layer l-1 +] conv of layer l: D[cout][pos] = sum over taps and input-channel k-steps ----
+        if (with_bott || (ksteps & 3) != 0) prewait1(); else prewait2();
+        wait_dep(l == 0, (uint32_t)pr);
+        if (with_bott) issue_bott();
         if ((ksteps & 3) == 0) {
           // two ring stages (4 k-steps) per iteration: both full-barrier probes are in flight together and the four MMAs and
           // the two stage releases go out from one elected region — a single warp retires a dependent instruction only every
@@ -298,13 +398,11 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
               wait_w2(wi1, wp1);
               const uint32_t a0 = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w, a1 = (ring_lo + wi1 * (kStkStageBytes >> 4)) | a_lbo_w;
               if (elect_one()) {
-                if (do_mma) {
-                  umma_bf16(d_main, stk_desc(a0, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, acc);
-                  umma_bf16(d_main, stk_desc(a0 + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
-                  umma_bf16(d_main, stk_desc(a1, desc_hi), stk_desc(bd_lo + 2 * kStep, desc_hi), idesc_main, 1);
-                  umma_bf16(d_main, stk_desc(a1 + 256u, desc_hi), stk_desc(bd_lo + 3 * kStep, desc_hi), idesc_main, 1);
-                }
-                if (!no_w) { umma_commit(&wempty[wi]); umma_commit(&wempty[wi1]); }
+                umma_bf16(d_main, stk_desc(a0, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, acc);
+                umma_bf16(d_main, stk_desc(a0 + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
+                umma_bf16(d_main, stk_desc(a1, desc_hi), stk_desc(bd_lo + 2 * kStep, desc_hi), idesc_main, 1);
+                umma_bf16(d_main, stk_desc(a1 + 256u, desc_hi), stk_desc(bd_lo + 3 * kStep, desc_hi), idesc_main, 1);
+                umma_commit(&wempty[wi]); umma_commit(&wempty[wi1]);
               }
               __syncwarp();
               acc = 1;
@@ -321,7 +419,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
 #pragma unroll
             for (int u = 0; u < 2; ++u) {
               if (blk + u < total) {
-                if (do_mma && elect_one()) umma_bf16(d_main, stk_desc(a_lo + u * 256u, desc_hi), stk_desc(bd_lo | b_lbo_x, desc_hi), idesc_main, (blk + u) > 0);
+                if (elect_one()) umma_bf16(d_main, stk_desc(a_lo + u * 256u, desc_hi), stk_desc(bd_lo | b_lbo_x, desc_hi), idesc_main, (blk + u) > 0);
                 __syncwarp();
                 bd_lo += kStep;
                 if (++jj == ksteps) { jj = 0; bd_lo += dil - (uint32_t)ksteps * kStep; }
@@ -330,9 +428,10 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             stage_done();
           }
         }
-        op_done();
+        commit_acc();
+        mark_issued();
         // ---- residual 1x1: accumulates on x + b_res stored by the epilogue ----
-        if (residual) {
+        if (L.residual) {
           prewait2();
           wait_dep(false, 0);
           uint32_t bd_lo = x_lo | b_lbo_x;
@@ -341,105 +440,130 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             wait_w2(wi1, wp1);
             const uint32_t a0 = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w, a1 = (ring_lo + wi1 * (kStkStageBytes >> 4)) | a_lbo_w;
             if (elect_one()) {
-              if (do_mma) {
-                umma_bf16(d_main, stk_desc(a0, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, 1);
-                umma_bf16(d_main, stk_desc(a0 + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
-                umma_bf16(d_main, stk_desc(a1, desc_hi), stk_desc(bd_lo + 2 * kStep, desc_hi), idesc_main, 1);
-                umma_bf16(d_main, stk_desc(a1 + 256u, desc_hi), stk_desc(bd_lo + 3 * kStep, desc_hi), idesc_main, 1);
-              }
-              if (!no_w) { umma_commit(&wempty[wi]); umma_commit(&wempty[wi1]); }
+              umma_bf16(d_main, stk_desc(a0, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, 1);
+              umma_bf16(d_main, stk_desc(a0 + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
+              umma_bf16(d_main, stk_desc(a1, desc_hi), stk_desc(bd_lo + 2 * kStep, desc_hi), idesc_main, 1);
+              umma_bf16(d_main, stk_desc(a1 + 256u, desc_hi), stk_desc(bd_lo + 3 * kStep, desc_hi), idesc_main, 1);
+              umma_commit(&wempty[wi]); umma_commit(&wempty[wi1]);
             }
             __syncwarp();
             bd_lo += 4 * kStep;
             adv2(wi1, wp1);
           }
-          op_done();
-        }
-        // ---- bottleneck 1x1, positions-as-M orientation: A = activation rows (two 128-row tiles), B = weights ----
-        if (highway) {
-          prewait1();
-          wait_dep(false, 0);
-          uint32_t xa_lo = x_lo | b_lbo_x;
-          for (int blk = 0; blk < kKC / 2; blk += bott_per_stage) {
-            wait_w();
-            const uint32_t w_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | b_lbo_bott;
-            if (elect_one()) {
-              uint32_t xa = xa_lo, wl = w_lo;
-              for (int u = 0; u < bott_per_stage; ++u) {
-                if (do_mma) {
-                  umma_bf16(d_main, stk_desc(xa, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
-                  umma_bf16(d_main + (uint32_t)p.bott, stk_desc(xa + 128u, desc_hi), stk_desc(wl, desc_hi), idesc_bott, (blk + u) > 0);
-                }
-                xa += kStep;
-                wl += (uint32_t)p.bott * 2u;
-              }
-              if (!no_w) umma_commit(&wempty[wi]);
-            }
-            __syncwarp();
-            xa_lo += (uint32_t)bott_per_stage * kStep;
-            if (++wi == kStkStages) { wi = 0; wp ^= 1; }
-          }
-          op_done();
+          commit_acc();
+          mark_issued();
         }
       }
+      // ---- bottleneck of the segment's last layer: an op of its own (the next conv belongs to the next read) ----
+      if (highway) {
+        prewait1();
+        wait_dep(false, 0);
+        issue_bott();
+        mark_issued();
+      }
     }
-    if (prof_on && lane == 0) { p.prof[blockIdx.x * 16 + 0 + 10 * s] = clock64() - t_begin; p.prof[blockIdx.x * 16 + 1 + 10 * s] = t_dep; p.prof[blockIdx.x * 16 + 12 + s] = t_wfull; }
+    STK_PROF(0);
+#ifdef DAN_STK_PROF
+    prof_acc[9] = clock64() - prof_begin;
+#endif
+    STK_PROF_FLUSH(lane == 0, 14 * s);
   }
   } else {
-#ifndef DAN_STK_NO_SETMAXNREG
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(kStkRegsEpi));
-#endif
-    // ===================== epilogue warps of slot s: quadrant q = TMEM lanes / channels 32q.., half h = position range;
-    // thread 0 of the slot's group also moves the slot's reads in and out ==========================================
+    // ===================== epilogue warps of slot s: quadrant q = TMEM lanes / channels 32q.., half h = position range; the slot's
+    // 8 warps also move the slot's reads in (bulk loads or the encoder) and out (bulk stores / reductions) ===============================
     const int s = warp >> 3, h = (warp >> 2) & 1, q = warp & 3;
     const int gtid = threadIdx.x & (kStkEpiThreads - 1);
-    const uint32_t tbase = tmem_base + (uint32_t)s * 256u + ((uint32_t)(32 * q) << 16);
-    const uint32_t buf_addr = smem_u32(bufs + (size_t)s * kStkBuf);
+    const int wl = warp & 7;            // this warp's index within the slot's epilogue group
+    const uint32_t tbase = tmem_base + (uint32_t)s * kStkAccStride + ((uint32_t)(32 * q) << 16);
+    const uint32_t tbott = tmem_base + (uint32_t)(h ? kStkBottCol1 : kStkBottCol0) + ((uint32_t)(32 * q) << 16);
+    uint8_t* const buf = bufs + (size_t)s * kStkBuf;
+    const uint32_t buf_addr = smem_u32(buf);
     // stmatrix / ldmatrix row address of this thread for position group 0: matrix lane>>3 = chunk plane 4q + (lane>>3), row lane&7
     const uint32_t saddr0 = buf_addr + (uint32_t)(4 * q + (lane >> 3)) * kStkPlane + (uint32_t)(kStkLead + (lane & 7)) * 16;
     const int g_begin = h == 0 ? 0 : 14, g_end = h == 0 ? 14 : 26;
-    // x += pool (model.py:734-742: the read-axis mean of the previous layer's output is added to the input of this segment's first
-    // layer). Runs on the freshly loaded read before the slot is handed to the issuer; bf16(x + pool) like the stand-alone kernel.
-    int tr_n = 0;
-    auto add_pool = [&](int read_local, uint32_t parity) {
-      mbar_wait(&sm->in_full[s], parity);
-      if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 7u << 24);     // the read has landed
-      const long cand = (long)(r_begin + read_local) / p.reads_per_cand;
-      const float* pl = p.pool + cand * kKC * p.P * 8;
-      uint8_t* b = bufs + (size_t)s * kStkBuf + kStkLead * 16;
-      for (int pos = gtid; pos < p.P; pos += kStkEpiThreads) {
-#pragma unroll 4
-        for (int kc = 0; kc < kKC; ++kc) {
-          uint4* px = reinterpret_cast<uint4*>(b + (size_t)kc * kStkPlane) + pos;
-          const float4* pa = reinterpret_cast<const float4*>(pl + ((long)kc * p.P + pos) * 8);
-          const float4 a0 = __ldg(pa), a1 = __ldg(pa + 1);
-          uint4 v = *px;
-          v.x = pack_bf16x2(bf16_lo(v.x) + a0.x, bf16_hi(v.x) + a0.y); v.y = pack_bf16x2(bf16_lo(v.y) + a0.z, bf16_hi(v.y) + a0.w);
-          v.z = pack_bf16x2(bf16_lo(v.z) + a1.x, bf16_hi(v.z) + a1.y); v.w = pack_bf16x2(bf16_lo(v.w) + a1.z, bf16_hi(v.w) + a1.w);
-          *px = v;
+
+    // brings the read `it` of this slot into the buffer (or arranges for it): encode mode = synchronous (bytes fetched earlier);
+    // planes mode = arm the barrier, lane 0 of every warp issues the bulk loads of two chunk planes (a bulk-copy instruction costs its
+    // issuing thread ~170 cycles, so the 2 x kc_in of them are spread over the slot's 8 warps)
+    auto prepare_read = [&](const StkIter& it, StkEncBytes eb) {
+      const bool valid = it.valid(p.R, s);
+      if (p.in_mode == kStkInEncode) {
+        if (valid) stk_enc_write(p, p.cand0 + it.cand, gtid, s, eb, buf);   // both named-barrier reductions inside are warp-uniformly reached
+        fence_proxy_async_smem();
+      } else {
+        if (gtid == 0) mbar_expect_tx(&sm->in_full[s], valid ? plane_bytes * in_kc : 0u);
+        named_bar_sync(1 + s, kStkEpiThreads);                      // the barrier is armed before any copy can complete
+        if (lane == 0 && valid) {
+          const uint4* src = p.in + kLead + ((long)it.cand * p.R + it.read_in_cand(s)) * p.pitch;
+          uint8_t* dst = buf + kStkLead * 16;
+          const uint64_t once = l2_policy_evict_first();          // activations stream through: read once, written once
+          for (int kc = 2 * wl; kc < 2 * wl + 2 && kc < in_kc; ++kc)
+            bulk_g2s_hint(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes, &sm->in_full[s], once);
         }
       }
-      fence_proxy_async_smem();
     };
-    const int wl = warp & 7;            // this warp's index within the slot's epilogue group
-    if (s < n_reads) {
-      if (gtid == 0) arm_read(s);
-      named_bar_sync(1 + s, kStkEpiThreads);
-      if (lane == 0) { load_read_planes(s, wl); if (s + 2 < n_reads) prefetch_read_planes(s + 2, wl); }
+    auto fetch_read = [&](const StkIter& it) -> StkEncBytes {
+      if (it.done() || !it.valid(p.R, s)) return 0u;
+      if (p.in_mode == kStkInEncode) return stk_enc_fetch(p, p.cand0 + it.cand, it.read_in_cand(s), gtid);
+      if (lane == 0) {                                                                 // L2 prefetch: the load itself is then an L2 hit
+        const uint4* src = p.in + kLead + ((long)it.cand * p.R + it.read_in_cand(s)) * p.pitch;
+        for (int kc = 2 * wl; kc < 2 * wl + 2 && kc < in_kc; ++kc) bulk_prefetch_l2(src + kc * p.in_kstride, plane_bytes);
+      }
+      return 0u;
+    };
+    // bottleneck epilogue of layer lb: tile h, TMEM lane = position 128h + 32q + lane, columns = bottleneck channels; relu(. + bias) -> T
+    uint32_t bfc = 0;
+    STK_PROF_DECL;
+    auto bott_epilogue = [&](int lb, int read_global, bool valid) {
+      STK_PROF(0);
+      mbar_wait(&sm->bott_full[s], bfc & 1);
+      ++bfc;
+      tc_fence_after();
+      STK_PROF(1);
+      uint32_t r[32];
+      tmem_ld32(tbott, r);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (atomicAdd(&sm->bott_drained, 1u) == kStkEpiThreads - 1) {      // the accumulator has been read out by all: the next bottleneck MMAs (either slot) may overwrite it
+        sm->bott_drained = 0;
+        __threadfence_block();
+        atomicExch(&sm->bott_busy, 0u);
+      }
+      const int pos = 128 * h + 32 * q + lane;
+      if (valid && pos < p.P) {
+        const float* bb = &sm->bbias[lb][0];
+        uint4* dst = p.layer[lb].tout + ((long)read_global * (kStkBott / 8)) * p.P + pos;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          uint4 o;                                                                 // relu(bottleneck), model.py:774
+          o.x = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 0]) + bb[g * 8 + 0], 0.f), fmaxf(__uint_as_float(r[g * 8 + 1]) + bb[g * 8 + 1], 0.f));
+          o.y = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 2]) + bb[g * 8 + 2], 0.f), fmaxf(__uint_as_float(r[g * 8 + 3]) + bb[g * 8 + 3], 0.f));
+          o.z = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 4]) + bb[g * 8 + 4], 0.f), fmaxf(__uint_as_float(r[g * 8 + 5]) + bb[g * 8 + 5], 0.f));
+          o.w = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 6]) + bb[g * 8 + 6], 0.f), fmaxf(__uint_as_float(r[g * 8 + 7]) + bb[g * 8 + 7], 0.f));
+          dst[(long)g * p.P] = o;                                                  // lanes = consecutive positions: 512 contiguous bytes per warp store
+        }
+      }
+      STK_PROF(2);
+    };
+
+    StkIter it;
+    it.init(p.cands, p.R);
+    if (!it.done()) {
+      const StkEncBytes eb = fetch_read(it);
+      prepare_read(it, eb);
     }
-    if (p.pool && s < n_reads) add_pool(s, 0);
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
-    uint32_t opc = 0, eops = 0;
-    long long t_wait = 0, t_main = 0, t_bott = 0, t_io = 0, t0 = 0;
-    const bool prof = prof_on && gtid == 0;
-    for (int i = s; i < n_reads; i += 2) {
-      for (int l = 0; l < p.num_layers; ++l) {
+    uint32_t opc = 0;
+    while (!it.done()) {
+      const bool valid = it.valid(p.R, s);
+      const int cand = it.cand;
+      const int read_global = cand * p.R + it.read_in_cand(s);
+      StkEncBytes eb_next = 0u;
+      for (int l = 0; l < n_layers; ++l) {
         const StackLayer& L = p.layer[l];
         const bool with_bmap = l == 0 && p.bmap != nullptr;     // the conv bias arrives inside the per-candidate pool bias map
-        const bool last = l + 1 == p.num_layers;
-        // without a bottleneck the layer's main epilogue is the read's last op: when the next read still gets the pool table added in
-        // shared memory, the hand-over to the issuer has to wait for that (the issuer only waits for act_ready and the load)
-        const bool defer_ready = last && !L.highway && p.pool != nullptr;
+        const bool last = l + 1 == n_layers;
         EpiConsts k;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -453,108 +577,76 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         uint4 bpre[4][2];
         const uint4* bm = nullptr;
         if (with_bmap) {
-          const long cand = (long)(r_begin + i) / p.reads_per_cand;
-          bm = p.bmap + (cand * 8 + (h * 4 + q)) * (7 * kStkBmapChunk) + lane * 2;
+          bm = p.bmap + ((long)cand * 8 + (h * 4 + q)) * (7 * kStkBmapChunk) + lane * 2;
 #pragma unroll
           for (int c = 0; c < 4; ++c) { bpre[c][0] = __ldg(bm + c * kStkBmapChunk); bpre[c][1] = __ldg(bm + c * kStkBmapChunk + 1); }
         }
-        if (prof) t0 = clock64();
+        if (highway && l > 0) bott_epilogue(l - 1, read_global, valid);      // runs under this layer's conv MMAs
+        if (last) { StkIter nxt = it; nxt.next(p.R); eb_next = fetch_read(nxt); }     // next read of this slot: bytes / L2 prefetch requested early
+        STK_PROF(0);
         mbar_wait(&sm->acc_full[s], opc & 1);
+        ++opc;
         tc_fence_after();
-        if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-        if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 3u << 24 | (eops & 0xFFFFu));
-        const bool do_epi = kDev == 0 || !(p.debug & 2);
-        if (!do_epi) {}
-        else if (with_bmap) stack_epi_bmap(tbase, saddr0, lane, p.P, g_begin, (g_end - g_begin) / 2, k, bm, bpre);
+        STK_PROF(3);
+        if (with_bmap) stack_epi_bmap(tbase, saddr0, lane, p.P, g_begin, (g_end - g_begin) / 2, k, bm, bpre);
         else if (L.residual) stack_epi_main<kEpiPreRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
         else stack_epi_main<kEpiFinal>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
         fence_proxy_async_smem();
         tc_fence_before();
-        if (L.residual || !defer_ready) mbar_arrive(&sm->act_ready[s]);
-        ++opc;
-        if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
-        if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
+        // without a bottleneck op behind it, the read's last hand-over doubles as "next read is in place" and is made at the boundary
+        if (L.residual || !last || highway) mbar_arrive(&sm->act_ready[s]);
+        STK_PROF(4);
         if (L.residual) {
           mbar_wait(&sm->acc_full[s], opc & 1);
+          ++opc;
           tc_fence_after();
-          if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 3u << 24 | (eops & 0xFFFFu));
-          if (do_epi) stack_epi_main<kEpiPostRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
+          STK_PROF(3);
+          stack_epi_main<kEpiPostRes>(tbase, saddr0, lane, p.P, g_begin, g_end, k);
           fence_proxy_async_smem();
           tc_fence_before();
-          if (!defer_ready) mbar_arrive(&sm->act_ready[s]);
-          ++opc;
-          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
-          if (prof) { const long long t1 = clock64(); t_main += t1 - t0; t0 = t1; }
-        }
-        if (last) {
-          // the segment output of this read is final: start writing it back now, under this layer's bottleneck MMA / epilogue
-          named_bar_sync(1 + s, kStkEpiThreads);
-          if (lane == 0) {           // two chunk planes per warp (bulk groups are per thread: each issuer commits and later waits for its own)
-            uint4* dst = p.out + kLead + (long)(r_begin + i) * p.pitch;
-            const uint8_t* src = bufs + (size_t)s * kStkBuf + kStkLead * 16;
-            const uint64_t once = l2_policy_evict_first();
-            for (int kc = 2 * wl; kc < 2 * wl + 2; ++kc) bulk_s2g_hint(dst + kc * p.out_kstride, src + (size_t)kc * kStkPlane, plane_bytes_in, once);
-            bulk_commit();
-          }
-        }
-        if (L.highway) {
-          mbar_wait(&sm->acc_full[s], opc & 1);
-          tc_fence_after();
-          if (prof) { const long long t1 = clock64(); t_wait += t1 - t0; t0 = t1; }
-          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 3u << 24 | (eops & 0xFFFFu));
-          // bottleneck tile h: TMEM lane = position 128h + 32q + lane, columns = bottleneck channels
-          const int c8n = p.bott / 8;
-          const int pos = 128 * h + 32 * q + lane;
-          bool handed_over = false;
-          for (int cc = 0; do_epi && cc < p.bott / 32; ++cc) {
-            uint32_t r[32];
-            tmem_ld32(tbase + (uint32_t)(h * p.bott + cc * 32), r);
-            tmem_ld_wait();
-            if (!last && cc + 1 == p.bott / 32) {
-              // the accumulator has been read out: the next layer's conv MMAs (which overwrite these columns) may start while this
-              // thread still converts and stores its T rows
-              tc_fence_before();
-              mbar_arrive(&sm->act_ready[s]);
-              handed_over = true;
-            }
-            if (pos < p.P) {
-              const float* bb = &sm->bbias[l][cc * 32];
-#pragma unroll
-              for (int g = 0; g < 4; ++g) {
-                uint4 o;                                                                 // relu(bottleneck), model.py:774
-                o.x = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 0]) + bb[g * 8 + 0], 0.f), fmaxf(__uint_as_float(r[g * 8 + 1]) + bb[g * 8 + 1], 0.f));
-                o.y = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 2]) + bb[g * 8 + 2], 0.f), fmaxf(__uint_as_float(r[g * 8 + 3]) + bb[g * 8 + 3], 0.f));
-                o.z = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 4]) + bb[g * 8 + 4], 0.f), fmaxf(__uint_as_float(r[g * 8 + 5]) + bb[g * 8 + 5], 0.f));
-                o.w = pack_bf16x2(fmaxf(__uint_as_float(r[g * 8 + 6]) + bb[g * 8 + 6], 0.f), fmaxf(__uint_as_float(r[g * 8 + 7]) + bb[g * 8 + 7], 0.f));
-                if (kDev == 0 || !(p.debug & 4)) L.tout[((long)(r_begin + i) * c8n + cc * 4 + g) * p.P + pos] = o;     // lanes = consecutive positions: 512 contiguous bytes per warp store
-              }
-            }
-          }
-          tc_fence_before();
-          if (!last && !handed_over) mbar_arrive(&sm->act_ready[s]);
-          ++opc;
-          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 4u << 24 | (eops++ & 0xFFFFu));
-          if (prof) { const long long t1 = clock64(); t_bott += t1 - t0; t0 = t1; }
-        }
-        if (last) {
-          // every MMA of this read has completed (the last accumulator was awaited above) and the write-back has been issued:
-          // refill the slot as soon as the store has read the buffer
-          if (lane == 0) bulk_wait_read0();                       // this warp's planes have been read out of the buffer
-          if (gtid == 0 && i + 2 < n_reads) arm_read(i + 2);
-          named_bar_sync(1 + s, kStkEpiThreads);                  // all planes drained, barrier armed
-          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 6u << 24 | (eops & 0xFFFFu));     // the store has drained the buffer
-          if (lane == 0 && i + 2 < n_reads) load_read_planes(i + 2, wl);
-          if (p.pool && i + 2 < n_reads) add_pool(i + 2, (uint32_t)((i + 2) >> 1) & 1u);
-          if (L.highway || defer_ready) mbar_arrive(&sm->act_ready[s]);
-          if (lane == 0 && i + 4 < n_reads) prefetch_read_planes(i + 4, wl);      // off the critical path: after the hand-over
-          if (trace_on && gtid == 0) stk_trace(p, 2 + s, tr_n, (uint32_t)s << 28 | 5u << 24 | (eops & 0xFFFFu));
-          if (prof) { const long long t1 = clock64(); t_io += t1 - t0; t0 = t1; }
+          if (!last || highway) mbar_arrive(&sm->act_ready[s]);
+          STK_PROF(5);
         }
       }
+      // ---- the read's segment output is final: hand its planes to the TMA engine (store / read-axis reductions), under the last
+      // bottleneck MMA / epilogue. Two chunk planes per warp (bulk groups are per thread: each issuer commits and waits for its own).
+      named_bar_sync(1 + s, kStkEpiThreads);
+      STK_PROF(10);
+      if (lane == 0 && valid) {
+        bulk_wait0();                                                     // earlier reductions into the same accumulators have landed (long ago)
+        STK_PROF(11);
+        const uint8_t* src = buf + kStkLead * 16;
+        const bool first_of_group = it.pr == 0;
+        const uint64_t once = l2_policy_evict_first();
+        for (int kc = 2 * wl; kc < 2 * wl + 2; ++kc) {
+          const uint8_t* sp = src + (size_t)kc * kStkPlane;
+          if (p.out) bulk_s2g_hint(p.out + kLead + (long)read_global * p.pitch + kc * p.out_kstride, sp, plane_bytes, once);
+          if (p.maxv) bulk_reduce_max_bf16(p.maxv + cand * p.max_stride + (long)kc * p.P, sp, plane_bytes);
+          if (p.sums) {
+            uint4* dst = p.sums + (((long)cand * p.groups_per_cand + it.group(s)) * kKC + kc) * p.P;
+            if (first_of_group) bulk_s2g(dst, sp, plane_bytes); else bulk_reduce_add_bf16(dst, sp, plane_bytes);
+          }
+        }
+        bulk_commit();
+      }
+      STK_PROF(6);
+      if (highway) bott_epilogue(n_layers - 1, read_global, valid);
+      // ---- read boundary: refill the slot as soon as the TMA engine has read the buffer ----
+      STK_PROF(0);
+      if (lane == 0) bulk_wait_read0();
+      named_bar_sync(1 + s, kStkEpiThreads);
+      STK_PROF(7);
+      it.next(p.R);
+      if (!it.done()) prepare_read(it, eb_next);
+      STK_PROF(8);
+      mbar_arrive(&sm->act_ready[s]);
+      STK_PROF(12);
     }
+#ifdef DAN_STK_PROF
+    prof_acc[9] = clock64() - prof_begin;
+#endif
+    STK_PROF_FLUSH(gtid == 0, 28 + 14 * s);
     if (lane == 0) bulk_wait0();
-    if (prof) { unsigned long long* d = p.prof + blockIdx.x * 16 + 2 + 3 * s; d[0] = t_wait; d[1] = t_main; d[2] = t_bott; p.prof[blockIdx.x * 16 + 8 + s] = t_io; }
   }
   tc_fence_before();
   __syncthreads();

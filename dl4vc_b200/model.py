@@ -251,6 +251,14 @@ class Basic2DNet(nn.Module):
                 _lib.check(_lib.load_library().dan_model_set_pass_candidates(st.handle, int(n)), "set_pass_candidates")
         return self
 
+    def set_layerwise(self, on: bool = True):
+        """Test hook: run the bf16 path layer by layer (the route of configurations the fused conv-stack kernel does not take)."""
+        self._flags = _lib.FLAG_LAYERWISE if on else 0
+        for st in self._native.values():
+            if st.handle:
+                _lib.check(_lib.load_library().dan_model_set_flags(st.handle, self._flags), "set_flags")
+        return self
+
     def _device(self) -> torch.device:
         dev = self.embeddings.weight.device
         if dev.type != "cuda":
@@ -274,6 +282,8 @@ class Basic2DNet(nn.Module):
                 st.handle = h
                 if getattr(self, "_pass_candidates", None):
                     _lib.check(lib.dan_model_set_pass_candidates(h, self._pass_candidates), "set_pass_candidates")
+                if getattr(self, "_flags", 0):
+                    _lib.check(lib.dan_model_set_flags(h, self._flags), "set_flags")
             fp = self._fingerprint()
             if st.fingerprint != fp:
                 self._pack(st, dev)
@@ -420,8 +430,9 @@ class Basic2DNet(nn.Module):
                 self.bin_output_weights, self.vt_output_weights, None, None, None, None)
 
     # ---- test hooks ---------------------------------------------------------------------------------------
-    def encode(self, reads, ref, q_scores=None, strands=None, ref_masks=None, var_masks=None):
-        """conv-1 input tensor in the reference's logical order (B, Cin, reads, positions) fp32 (model.py:719)."""
+    def encode(self, reads, ref, q_scores=None, strands=None, ref_masks=None, var_masks=None, bf16=False):
+        """conv-1 input tensor in the reference's logical order (B, Cin, reads, positions) fp32 (model.py:719). bf16=True: what the fused
+        bf16 kernel's encoder prologue builds (bf16 values, widened)."""
         dev = self._device()
         lib = _lib.load_library()
         with torch.cuda.device(dev):
@@ -434,8 +445,9 @@ class Basic2DNet(nn.Module):
             rm8 = self._u8(ref_masks, dev) if self.use_reads_ref_var_mask else None
             vm8 = self._u8(var_masks, dev) if self.use_reads_ref_var_mask else None
             p = lambda t: None if t is None else t.data_ptr()
-            _lib.check(lib.dan_encode(st.handle, p(r8), p(q8), p(s8), p(f8), p(rm8), p(vm8), B, out.data_ptr(),
-                                      torch.cuda.current_stream(dev).cuda_stream), "dan_encode")
+            fn = lib.dan_encode_bf16 if bf16 else lib.dan_encode
+            _lib.check(fn(st.handle, p(r8), p(q8), p(s8), p(f8), p(rm8), p(vm8), B, out.data_ptr(),
+                          torch.cuda.current_stream(dev).cuda_stream), "dan_encode")
         return out
 
     def debug_fc_input(self, batch: int):

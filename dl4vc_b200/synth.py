@@ -26,6 +26,7 @@ class PileupBatch:
     var_masks: np.ndarray  # (B, 201) uint8
     num_reads: np.ndarray  # (B,) int32 populated rows
     kind: np.ndarray       # (B,) uint8  0 SNP, 1 insert, 2 delete
+    var_fraction: np.ndarray = None   # (B,) float32 planted share of reads carrying the proposed allele: 0 / 0.5 / 1 (a genotype label)
 
     def __len__(self):
         return self.reads.shape[0]
@@ -35,7 +36,8 @@ class PileupBatch:
 
     def slice(self, lo, hi):
         return PileupBatch(*(a[lo:hi] for a in (self.reads, self.q_scores, self.strands, self.ref, self.ref_masks,
-                                                 self.var_masks, self.num_reads, self.kind)))
+                                                 self.var_masks, self.num_reads, self.kind)),
+                           var_fraction=None if self.var_fraction is None else self.var_fraction[lo:hi])
 
     @property
     def nbytes(self):
@@ -120,7 +122,7 @@ def make_pileups(n: int, seed: int = 20261018, num_reads: int = 100, coverage: s
     strands = np.where(inside, strand_of_read[..., None], 0).astype(np.uint8)
 
     tr = lambda a: np.ascontiguousarray(a.transpose(0, 2, 1))
-    return PileupBatch(tr(reads), tr(q), tr(strands), ref, ref_masks, var_masks, depth.astype(np.int32), kind)
+    return PileupBatch(tr(reads), tr(q), tr(strands), ref, ref_masks, var_masks, depth.astype(np.int32), kind, frac.astype(np.float32))
 
 
 def edge_case_pileups(num_reads: int = 100) -> PileupBatch:

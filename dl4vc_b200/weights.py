@@ -33,8 +33,28 @@ def _rng(seed: int, name: str) -> np.random.Generator:
     return np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
 
 
-def synth_state_dict(cfg: DanConfig, seed: int = 1, head_gain: float = 8.0, as_torch: bool = True, prefix: str = ""):
-    """name -> tensor for every entry of state_dict_spec(cfg)."""
+def plant_tracer_channels(cfg: DanConfig, sd: dict, gain: float = 2.0):
+    """Make the stack sensitive to the genotype evidence, the way a trained checkpoint is: output channels 0 / 1 of every non-residual
+    conv layer carry the var-match / ref-match input channels (model.py:576-625) straight through (centre tap, zero bias; ReLU is the
+    identity on these non-negative values, BatchNorm stays an affine map with the layer's own statistics), and the residual layers add
+    their usual terms on top. The read-mean of those channels at the proposal columns is then an affine function of the share of reads
+    that support the proposed / reference allele — the signal the classification heads of the scale golden are fitted on
+    (oracle/make_scale_golden.py). numpy arrays in, modified in place."""
+    assert cfg.use_reads_ref_var_mask
+    first = 2 * cfg.embed_dim + int(cfg.use_q_scores) + int(cfg.use_strands)      # ref-match channel; var-match is first + 1
+    for l in range(cfg.total_conv_layers):
+        if cfg.is_residual(l + 1):
+            break
+        w, b = sd[f"conv1D_layers.{l}.weight"], sd[f"conv1D_layers.{l}.bias"]
+        for out_ch, src in ((0, first + 1 if l == 0 else 0), (1, first if l == 0 else 1)):
+            w[out_ch] = 0.0
+            w[out_ch, src, 0, 1] = gain
+            b[out_ch] = 0.0
+    return sd
+
+
+def synth_state_dict(cfg: DanConfig, seed: int = 1, head_gain: float = 8.0, as_torch: bool = True, prefix: str = "", tracer: bool = False):
+    """name -> tensor for every entry of state_dict_spec(cfg). tracer: see plant_tracer_channels."""
     out = {}
     spec = state_dict_spec(cfg)
     shapes = {n: s for n, s, _ in spec}
@@ -73,6 +93,9 @@ def synth_state_dict(cfg: DanConfig, seed: int = 1, head_gain: float = 8.0, as_t
                 gain = math.sqrt(3.0)  # keep post-ReLU activations O(1) through 7 layers
             a = g.uniform(-bound * gain, bound * gain, shape).astype(np.float32)
         out[prefix + name] = a
+    if tracer:
+        assert not prefix
+        plant_tracer_channels(cfg, out)
     if as_torch:
         import torch
 

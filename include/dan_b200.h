@@ -102,6 +102,12 @@ int dan_model_load_weights(dan_model* m, const dan_weights* w, void* stream);
 /* Number of candidates the conv stack processes per internal pass (activations of one pass stay L2-resident). */
 int dan_model_set_pass_candidates(dan_model* m, int candidates);
 
+/* Test hook: behaviour switches of a model handle. DAN_FLAG_LAYERWISE makes the bf16 path run its layer-by-layer kernels (the
+ * route of the configurations the fused conv-stack kernel does not take) on every configuration, so that both routes can be
+ * compared on the same inputs. */
+enum { DAN_FLAG_LAYERWISE = 1 };
+int dan_model_set_flags(dan_model* m, int flags);
+
 /* Bytes of device scratch dan_forward needs for a batch of `batch` candidates at `precision`. */
 size_t dan_workspace_bytes(const dan_model* m, int batch, int precision);
 
@@ -161,6 +167,13 @@ int dan_make_mask_vectors(const char* const* ref_alleles, const char* const* var
 int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
                const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks, int batch,
                float* x0_out, void* stream);
+
+/* Same hook for the bf16 path: what the fused conv-stack kernel's encoder prologue builds in shared memory for every read (bf16
+ * planes, 45 -> 48 channels), widened to fp32 in the same (batch, Cin, num_reads, read_len) order — bf16_rn of the reference values,
+ * match masks exactly 0 / 1. DAN_E_UNSUPPORTED for channel sets other than the shipped one (those use the fp32 encoder's rows). */
+int dan_encode_bf16(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
+                    const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks, int batch,
+                    float* x0_out, void* stream);
 
 /* Test hook: after a dan_forward call on `workspace`, copy the FC input vector (pooled max|mean|relu(highway),
  * dl4vc/model.py:838-912) of the LAST internal pass to out (rows x fc_in_features fp32, DEVICE pointer).

@@ -1,14 +1,3 @@
 #!/bin/bash
-# development: per-role cycle counters of the fused stack kernel + a short bench
-set -u
-mkdir -p gpurun_out
-DAN_B200_STACKPROF=1 timeout 300 python bench.py --steps 1 --warmup 3 --batch 512 --no-cpu-baseline > gpurun_out/prof_bench.json 2> gpurun_out/prof_bench.err; echo "prof rc=$?"
-grep stackprof gpurun_out/prof_bench.err | tail -4
-timeout 300 python bench.py --steps ${STEPS:-3} --warmup 3 --batch ${BATCH:-2048} --no-cpu-baseline > gpurun_out/bench_quick.json 2> gpurun_out/bench_quick.err; echo "bench rc=$?"
-python - <<'PY'
-import json
-d=json.load(open('gpurun_out/bench_quick.json'))
-r=d['roofline']
-print('value',round(d['value']),'e2e',round(d['e2e']['value']),'conv frac',round(r['frac'],3),'classes',{k:round(v,1) for k,v in r['class_ms_per_step'].items()}, 'clk',d['clocks'])
-PY
-tail -3 gpurun_out/bench_quick.err
+# development: per-role cycle counters of the conv-stack kernel (library built with `python -m dl4vc_b200.build --prof`)
+DAN_B200_LIB=$PWD/dl4vc_b200/libdan_b200_prof.so timeout 300 python bench.py --steps 1 --warmup 1 --batch ${BATCH:-296} --no-cpu-baseline 2>&1 >/dev/null | grep stkprof | tail -${N:-8}

@@ -35,6 +35,34 @@ def test_encoder_bit_exact(golden):
     assert np.array_equal(digest, golden["x0_sha256"]), "conv-1 input differs from the reference bit pattern"
 
 
+def _bf16_rn(x):
+    """fp32 -> nearest-even bf16 -> fp32 (numpy)."""
+    u = np.ascontiguousarray(x, np.float32).view(np.uint32).astype(np.uint64)
+    u = ((u + 0x7FFF + ((u >> 16) & 1)) >> 16) << 16
+    return u.astype(np.uint32).view(np.float32)
+
+
+@pytest.mark.parametrize("name", ["prod_smallfc_mixed", "prod_smallfc_edge", "prod_full", "reads300_ragged"])
+def test_bf16_production_encoder_bit_exact(name):
+    """The encoder the benchmarked path actually runs (prologue of the fused conv-stack kernel: uint8 tiles -> bf16 planes in shared
+    memory) must produce exactly bf16_rn(reference conv-1 input): x0 is elementwise, so the rounded reference is an exact target.
+    The oracle's x0 is bit-identical to the reference's (tests/test_oracle_golden.py, SHA-256); match-mask channels must be exactly 0/1."""
+    g = load_golden(name)
+    cfg = g["cfg"]
+    sd = synth_state_dict(cfg, seed=g["seed"])
+    model = build_model(cfg, sd, precision="bf16")
+    r, q, s, ref, rm, vm = _tensors(g["arrays"])
+    got = model.encode(r, ref, q, s, rm, vm, bf16=True).cpu().numpy()
+    rr, qq, ss, rf, rmm, vmm = g["arrays"]
+    want = dan_oracle.encode(cfg, sd, rr, rf, qq, ss, rmm, vmm)
+    digest = np.frombuffer(hashlib.sha256(np.ascontiguousarray(want).tobytes()).digest(), dtype=np.uint8)
+    assert np.array_equal(digest, g["x0_sha256"]), "oracle x0 is not the reference's"
+    assert got.shape == want.shape
+    assert np.array_equal(got.view(np.uint32), _bf16_rn(want).view(np.uint32)), "bf16 conv-1 input differs from bf16_rn(reference)"
+    masks = got[:, 2 * cfg.embed_dim + 2:]
+    assert np.isin(masks, (0.0, 1.0)).all() and np.array_equal(masks, want[:, 2 * cfg.embed_dim + 2:])
+
+
 def test_fp32_heads_match_reference_goldens(golden):
     cfg = golden["cfg"]
     model = build_model(cfg, synth_state_dict(cfg, seed=golden["seed"]), precision="fp32")
@@ -246,15 +274,14 @@ def test_bf16_pool_bias_map_is_batch_shape_invariant():
     assert np.abs(full - ref32).max() / np.abs(ref32).max() < BF16_TOL
 
 
-def test_bf16_layerwise_fallback_agrees_with_fused_path(monkeypatch):
+def test_bf16_layerwise_fallback_agrees_with_fused_path():
     """Configurations the fused stack kernel does not take (window != 201, a residual layer right behind a pool-add) run layer by
     layer (dan_layer_kernel); the same inputs through both code paths must give the same numbers up to bf16 re-rounding."""
     g = load_golden("prod_smallfc_mixed")
     cfg = g["cfg"]
     model = build_model(cfg, synth_state_dict(cfg, seed=g["seed"]), precision="bf16")
     fused = _heads(model, g["arrays"])
-    monkeypatch.setenv("DAN_B200_LAYERWISE", "1")
-    layerwise = _heads(model, g["arrays"])
+    layerwise = _heads(model.set_layerwise(True), g["arrays"])
     assert rel_err(layerwise, g["heads"]) < BF16_TOL
     assert rel_err(layerwise, fused) < BF16_TOL
 
