@@ -616,12 +616,6 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
       SL.kc_in = (k == 0 ? m->CinPad : kC) / 8; SL.conv_blocks = 3 * SL.kc_in / 2;
       SL.dil = m->cfg.dilation[k]; SL.residual = m->cfg.is_residual[k];
     }
-    {
-      int ops = sp.highway ? 1 : 0;
-      for (int k = l; k < l_end; ++k) ops += 1 + (m->cfg.is_residual[k] ? 1 : 0);
-      static const int lag_env = getenv("DAN_B200_LAG") ? atoi(getenv("DAN_B200_LAG")) : 0;     // TEMPORARY (experiment)
-      sp.lag_ops = lag_env > 0 ? (lag_env < ops ? lag_env : ops) : (ops + 1) / 2;
-    }
     const int blocks = ns * (sum_groups_per_cand(m) / 2);
     const int grid = blocks < bw->num_sms ? blocks : bw->num_sms;
 #ifdef DAN_STK_PROF

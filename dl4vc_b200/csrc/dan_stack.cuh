@@ -44,7 +44,7 @@ constexpr int kStkRB = kStkLead + kStkN + 2;   // rows per channel-chunk plane o
 constexpr int kStkPlane = kStkRB * 16;         // bytes per plane (3392)
 constexpr int kStkBuf = kKC * kStkPlane;       // bytes per read buffer (54272)
 constexpr int kStkStageBytes = 8192;   // weight-ring stage = two k-step blocks of 4 KB
-constexpr int kStkStages = 7;          // stages of EACH slot's private weight ring (prefetch depth; a slot's ops never wait for the other slot's consumption)
+constexpr int kStkStages = 14;         // stages of the weight ring shared by the two slots (>= largest op (13) + prefetch)
 constexpr int kStkMaxSeg = 8;          // layers per segment
 constexpr int kStkRegsIssue = 56, kStkRegsEpi = 104;   // setmaxnreg redistributes the launch allocation (640 x 96): 128 x 56 + 512 x 104 = 60416 <= 61440
 constexpr int kStkBmapChunk = 64;       // uint4 per (role, 16-position chunk) of the pool bias map: 32 lanes x 2 (bmap_pack_kernel, dan_bf16.cu)
@@ -54,7 +54,7 @@ constexpr int kStkAccStride = 256;      // TMEM columns between the two slots' m
 constexpr int kStkBottCol0 = 224, kStkBottCol1 = 480;   // shared bottleneck accumulator: position tile 0 / 1 (32 columns each) in the gaps behind the main accumulators
 constexpr int kStkBlockReads = 20;      // work unit: consecutive reads of one candidate = one sum group per slot
 constexpr int kStkSmemHeader = 3072;    // barriers, TMEM pointer, bottleneck biases of the segment
-constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + 2 * kStkStages * kStkStageBytes;
+constexpr size_t kStkSmemBytes = kStkSmemHeader + 2 * (size_t)kStkBuf + kStkStages * kStkStageBytes;
 
 enum { kStkInPlanes = 0, kStkInEncode = 1 };
 
@@ -79,7 +79,6 @@ struct StackParams {
   uint4* maxv; long max_stride;         // optional: read-axis max [candidate * max_stride + (c/8) * P + p] pieces (bf16), pre-set to -inf
   const uint4* bmap;                    // optional pool bias map conv(pool) + bias of the segment's first layer, [candidate][kStkBmapPerCand]
   int cands, R, P, pitch, highway, num_layers;
-  int lag_ops;                          // slot 1 starts its op n once slot 0 has issued op n + lag_ops - 1 (>= 1): how far the two slots run out of phase
 #ifdef DAN_STK_PROF
   unsigned long long* prof;             // development build: [grid][48] cycle counters
 #endif
@@ -87,7 +86,7 @@ struct StackParams {
 };
 
 struct StackSmem {
-  uint64_t w_full[2][kStkStages], w_empty[2][kStkStages];
+  uint64_t w_full[kStkStages], w_empty[kStkStages];
   uint64_t acc_full[2], act_ready[2], in_full[2], bott_full[2];
   uint32_t bott_busy, bott_drained;    // the shared bottleneck accumulator: taken by an issuer (CAS 0 -> 1), given back by the last of the 256 epilogue threads that read it out
   uint32_t tmem_base;
@@ -215,7 +214,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     for (int i = threadIdx.x; i < 2 * kStkBuf / 16; i += kStkThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2 * kStkStages; ++i) { mbar_init(&sm->w_full[0][i], 1); mbar_init(&sm->w_empty[0][i], 1); }
+    for (int i = 0; i < kStkStages; ++i) { mbar_init(&sm->w_full[i], 1); mbar_init(&sm->w_empty[i], 2); }   // both slots release a stage
     sm->issued_ops = 0;
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sm->acc_full[s], 1); mbar_init(&sm->act_ready[s], kStkEpiThreads); mbar_init(&sm->in_full[s], 1); mbar_init(&sm->bott_full[s], 1);
@@ -240,21 +239,22 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
   if (warp >= 16) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(kStkRegsIssue));
   if (warp == 16 || warp == 17) {
-    // ===================== weight producers: lane 0 of warp 16 + s streams the layer weights of slot s's reads into that slot's ring
-    // (~300 cycles per stage: empty-barrier probe + expect_tx + copy issue; the tensor pipe drains a stage in ~210).
+    // ===================== weight producer: ONE stream for both slots (every stage is consumed twice before it is refilled, which
+    // halves the L2 -> SMEM weight traffic: measured ~100 W of board power against private per-slot rings at the same speed). Two
+    // producer threads (lane 0 of warps 16 and 17) take alternate stages: one thread needs ~300 cycles per stage (empty-barrier
+    // probe + expect_tx + copy issue), close to the rate at which the tensor pipe drains one.
     if (lane == 0) {
-      const int s = warp - 16;
-      uint64_t* const wfull = &sm->w_full[s][0];
-      uint64_t* const wempty = &sm->w_empty[s][0];
-      uint8_t* const ring = rings + (size_t)s * kStkStages * kStkStageBytes;
-      const uint64_t keep = l2_policy_evict_last();          // the weight images are re-read by every CTA for every read
-      uint32_t idx = 0, par = 1;              // first pass over the ring: the "empty" phase counts as complete
+      const uint32_t mine = (uint32_t)(warp - 16);
+      const uint64_t keep = l2_policy_evict_last();          // the weight images are re-read by every CTA for every pair of reads
+      uint32_t idx = 0, par = 1, seq = 0;     // first pass over the ring: the "empty" phase counts as complete
       auto emit = [&](const uint8_t* src, uint32_t bytes) {
         for (uint32_t off = 0; off < bytes; off += kStkStageBytes) {
-          const uint32_t n = min((uint32_t)kStkStageBytes, bytes - off);
-          mbar_wait(&wempty[idx], par);
-          mbar_expect_tx(&wfull[idx], n);
-          bulk_g2s_hint(ring + (size_t)idx * kStkStageBytes, src + off, n, &wfull[idx], keep);
+          if ((seq++ & 1u) == mine) {
+            const uint32_t n = min((uint32_t)kStkStageBytes, bytes - off);
+            mbar_wait(&sm->w_empty[idx], par);
+            mbar_expect_tx(&sm->w_full[idx], n);
+            bulk_g2s_hint(rings + (size_t)idx * kStkStageBytes, src + off, n, &sm->w_full[idx], keep);
+          }
           if (++idx == kStkStages) { idx = 0; par ^= 1; }
         }
       };
@@ -262,7 +262,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         for (int l = 0; l < n_layers; ++l) {
           const StackLayer& L = p.layer[l];
           const uint32_t conv_bytes = (uint32_t)L.conv_blocks * 4096u;
-          const uint8_t* w = L.wstream + (size_t)((2 * blockIdx.x + s) % kWeightReplicas) * L.wreplica_stride;
+          const uint8_t* w = L.wstream + (size_t)(blockIdx.x % kWeightReplicas) * L.wreplica_stride;
           emit(w, conv_bytes);
           if (L.residual) emit(w + conv_bytes, kKC / 2 * 4096u);
           if (highway) emit(w + conv_bytes + (L.residual ? kKC / 2 * 4096u : 0u), (uint32_t)kKC * kStkBott * 16u);
@@ -280,14 +280,11 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
     const uint32_t a_lbo_w = (2048u >> 4) << 16, b_lbo_x = ((uint32_t)kStkPlane >> 4) << 16, b_lbo_bott = (((uint32_t)kStkBott * 16u) >> 4) << 16;
     constexpr int kBottPerStage = kStkStageBytes / (kStkBott * 32);      // k-steps of bottleneck weights per ring stage (8 = all of them)
-    const uint32_t ring_lo = smem_u32(rings + (size_t)s * kStkStages * kStkStageBytes) >> 4;
-    uint64_t* const wfull = &sm->w_full[s][0];
-    uint64_t* const wempty = &sm->w_empty[s][0];
+    const uint32_t ring_lo = smem_u32(rings) >> 4;
+    uint64_t* const wfull = &sm->w_full[0];
+    uint64_t* const wempty = &sm->w_empty[0];
     volatile uint32_t* const issued = &sm->issued_ops;
     uint32_t gops = 0;                                                                            // ops started by this issuer
-    uint32_t total_ops = 0;
-    for (int l = 0; l < n_layers; ++l) total_ops += 1u + (p.layer[l].residual ? 1u : 0u);
-    total_ops = (total_ops + (highway ? 1u : 0u)) * (uint32_t)n_pairs;                           // ops of one slot over the whole launch
     const uint32_t d_main = tmem_base + (uint32_t)s * kStkAccStride, d_bott0 = tmem_base + kStkBottCol0, d_bott1 = tmem_base + kStkBottCol1;
     const uint32_t x_lo = (smem_u32(bufs) >> 4) + (uint32_t)s * (kStkBuf >> 4) + kStkLead;       // centre row of chunk plane 0
     constexpr uint32_t kStep = 2 * (kStkPlane >> 4);                                              // one k-step = two chunk planes
@@ -323,7 +320,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       // consumers of the shared weight ring stays within one op (<= 13 of the 14 stages).
       // (polled with a short sleep: a tight shared-memory spin would take issue slots from the epilogue warps of this warp's scheduler)
       STK_PROF(0);
-      if (s == 1) { const uint32_t need = min(gops + (uint32_t)p.lag_ops, total_ops); uint32_t spins = 0; while (*issued < need) { __nanosleep(32); if (++spins > (1u << 24)) __trap(); } }
+      if (s == 1) { uint32_t spins = 0; while (*issued <= gops) { __nanosleep(32); if (++spins > (1u << 24)) __trap(); } }
       ++gops;
       STK_PROF(2);
       mbar_wait(&sm->act_ready[s], opc & 1);
