@@ -402,6 +402,7 @@ inline bool stack_fused(const dan_model* m) {
   }
   return true;
 }
+constexpr int kCompSplits = 4;
 inline int sum_groups_per_cand(const dan_model* m) { return 2 * ((m->R + kStkBlockReads - 1) / kStkBlockReads); }
 
 // workspace carve-up ---------------------------------------------------------------------------------------
@@ -412,7 +413,7 @@ struct Bf16Plan {
   long hw_layer_stride;
   long t_layer_pieces;               // uint4 pieces of one layer's T matrix
   int fcKC;                          // FC input pieces
-  size_t off_zero_begin, off_x0, off_h[3], off_zero_end, off_t, off_pool, off_sums, off_im2col, off_bmapg, off_bmap, off_hw, off_fcin, off_fcx[DAN_MAX_FC], total;
+  size_t off_zero_begin, off_x0, off_h[3], off_zero_end, off_t, off_pool, off_sums, off_im2col, off_bmapg, off_bmap, off_hw, off_part, off_fcin, off_fcx[DAN_MAX_FC], total;
   int maxN;
 };
 
@@ -444,6 +445,7 @@ Bf16Plan make_plan(const dan_model* m, int batch) {
   pl.off_bmap = take((size_t)pl.S * kBmapBytesPerCand);      // conv(pool) + bias in the stack epilogue's fragment order, bf16 pairs
   pl.hw_layer_stride = pl.readsPad * bott;
   pl.off_hw = take((size_t)m->L * pl.hw_layer_stride * 4);
+  pl.off_part = take((size_t)kCompSplits * m->L * pl.readsPad * bott * 4);     // split-K partials of the compression GEMM
   pl.off_fcin = take((size_t)pl.fcKC * pl.BcPad * 16);           // [BcPad][fcInPad] bf16, row-major
   pl.maxN = DAN_HEAD_PAD;
   for (int i = 0; i < m->cfg.num_fc; ++i) {
@@ -585,6 +587,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
     Gemm2Operand B{bw->wcomp[l0], bott, K * 2, K * 2 * bott};
     Gemm2Params gp{};
     gp.M = reads; gp.N = bott; gp.K = (int)K; gp.mode = kG2Raw;
+    gp.part = reinterpret_cast<float*>(base + pl.off_part); gp.splits = kCompSplits;      // K = 6432 in 4 fixed ranges: same sums for every batch shape, 4x the CTAs
     gp.out = HW + (long)l0 * pl.hw_layer_stride; gp.out_batch_stride = pl.hw_layer_stride; gp.ldo = bott;
     return run_gemm2(A, B, gp, nl, bw->num_sms, st);
   };

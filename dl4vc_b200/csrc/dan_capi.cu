@@ -373,6 +373,47 @@ int dan_encode_bf16(dan_model* m, const uint8_t* reads, const uint8_t* q_scores,
   return dan_bf16_encode_reference_order(m, in, batch, x0_out, static_cast<cudaStream_t>(stream));
 }
 
+size_t dan_train_tape_bytes(const dan_model* m, int batch) {
+  if (!m || batch < 1 || !dan_train_supported(m)) return 0;
+  return dan_train_tape_bytes_impl(m, batch);
+}
+
+static int check_train_args(dan_model* m, const dan_weights* params, const uint8_t* reads, const uint8_t* q, const uint8_t* s, const uint8_t* ref,
+                            const uint8_t* rm, const uint8_t* vm, int batch, const void* out, float dropout_p) {
+  int rc = check_forward_args(m, DAN_PRECISION_FP32, reads, q, s, ref, rm, vm, batch, out);
+  if (rc) return rc;
+  if (!params) { dan_set_error("null parameter struct"); return DAN_E_INVALID; }
+  if (batch < 1) { dan_set_error("training needs at least one candidate"); return DAN_E_INVALID; }
+  if (!(dropout_p >= 0.f && dropout_p < 1.f)) { dan_set_error("dropout probability %g outside [0, 1)", dropout_p); return DAN_E_INVALID; }
+  if (!dan_train_supported(m)) { dan_set_error("training kernels do not cover this configuration (pool_combine_dimension > 0)"); return DAN_E_UNSUPPORTED; }
+  for (int l = 0; l < m->L; ++l)
+    if (m->cfg.use_batchnorm && (!params->bn_w[l] || !params->bn_b[l] || !params->bn_mean[l] || !params->bn_var[l])) { dan_set_error("missing BatchNorm tensors of layer %d", l + 1); return DAN_E_INVALID; }
+  return DAN_OK;
+}
+
+int dan_train_forward(dan_model* m, const dan_weights* params, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
+                      const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks, const uint8_t* removed, int batch,
+                      float dropout_p, uint64_t seed, float* heads_out, void* tape, size_t tape_bytes, void* stream) {
+  g_launches = 0;
+  int rc = check_train_args(m, params, reads, q_scores, strands, ref, ref_masks, var_masks, batch, heads_out, dropout_p);
+  if (rc) return rc;
+  if (!tape) { dan_set_error("null tape"); return DAN_E_WORKSPACE; }
+  DevInputs in{reads, q_scores, strands, ref, ref_masks, var_masks};
+  return dan_train_forward_impl(m, params, in, removed, batch, dropout_p, seed, heads_out, tape, tape_bytes, static_cast<cudaStream_t>(stream));
+}
+
+int dan_backward(dan_model* m, const dan_weights* params, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
+                 const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks, const uint8_t* removed, int batch,
+                 float dropout_p, uint64_t seed, const float* dheads, const float* heads_out, const dan_weights* grads,
+                 void* tape, size_t tape_bytes, void* stream) {
+  g_launches = 0;
+  int rc = check_train_args(m, params, reads, q_scores, strands, ref, ref_masks, var_masks, batch, heads_out, dropout_p);
+  if (rc) return rc;
+  if (!tape || !dheads || !grads) { dan_set_error("null tape / gradient pointer"); return DAN_E_INVALID; }
+  DevInputs in{reads, q_scores, strands, ref, ref_masks, var_masks};
+  return dan_backward_impl(m, params, in, removed, batch, dropout_p, seed, dheads, heads_out, grads, tape, tape_bytes, static_cast<cudaStream_t>(stream));
+}
+
 int dan_scores(const float* heads, int batch, float* scores_out, void* stream) {
   if (batch < 0) { dan_set_error("negative batch"); return DAN_E_INVALID; }
   if (batch == 0) return DAN_OK;

@@ -21,7 +21,8 @@ struct Gemm2Params {
   int M, N, K;                         // per batch entry
   int m_tiles, n_tiles, splits, batch;
   int mode;
-  float* out; long out_batch_stride; int ldo;          // kG2Raw: fp32 [batch][M][ldo] (atomicAdd when splits > 1); kG2Heads: fp32 [M][27]
+  float* out; long out_batch_stride; int ldo;          // kG2Raw: fp32 [batch][M][ldo]; kG2Heads: fp32 [M][27]
+  float* part;                                         // kG2Raw with splits > 1 (set by the caller): partial sums [split][batch][M][N], added in split order by splitk_reduce_kernel
   const float* bias;                                   // modes 1, 2
   __nv_bfloat16* out_bf16; int ld_bf16;                // kG2BiasReluBf16: bf16 [M][ld_bf16]
 };
@@ -129,15 +130,11 @@ __global__ void __launch_bounds__(kG2Threads, 1) tma_gemm_kernel(const __grid_co
         if (row < p.M) {
           const int n0 = n_tile * BN + c * 32;
           if (p.mode == kG2Raw) {
-            float* orow = p.out + (long)b * p.out_batch_stride + (long)row * p.ldo + n0;
-            if (p.splits > 1) {
+            float* orow = p.splits > 1 ? p.part + (((long)split * p.batch + b) * p.M + row) * p.N + n0
+                                       : p.out + (long)b * p.out_batch_stride + (long)row * p.ldo + n0;
 #pragma unroll
-              for (int j = 0; j < 32; ++j) atomicAdd(orow + j, __uint_as_float(r[j]));
-            } else {
-#pragma unroll
-              for (int j = 0; j < 32; j += 4)
-                *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            }
+            for (int j = 0; j < 32; j += 4)
+              *reinterpret_cast<float4*>(orow + j) = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
           } else if (p.mode == kG2BiasReluBf16) {
             uint4* orow = reinterpret_cast<uint4*>(p.out_bf16 + (long)row * p.ld_bf16 + n0);
 #pragma unroll
@@ -166,6 +163,17 @@ __global__ void __launch_bounds__(kG2Threads, 1) tma_gemm_kernel(const __grid_co
   }
   __syncthreads();
   if (warp == 1) tmem_dealloc<(BN < 32 ? 32 : BN)>(tmem_base);
+}
+
+// fixed-order sum of the split-K partials (a candidate's numbers must not depend on the batch it arrives in)
+__global__ void splitk_reduce_kernel(const float* __restrict__ part, int splits, int batch, int M, int N, float* __restrict__ out, long out_batch_stride, int ldo) {
+  const long total = (long)batch * M * N;
+  for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    float v = 0.f;
+    for (int s = 0; s < splits; ++s) v += part[(long)s * total + i];
+    const int n = (int)(i % N); const long t = i / N; const int row = (int)(t % M); const int b = (int)(t / M);
+    out[(long)b * out_batch_stride + (long)row * ldo + n] = v;
+  }
 }
 
 // ---- host side ---------------------------------------------------------------------------------------------------
@@ -215,23 +223,23 @@ int run_gemm2(const Gemm2Operand& A, const Gemm2Operand& B, Gemm2Params g, int b
   g.batch = batch;
   g.m_tiles = (g.M + 127) / 128; g.n_tiles = g.N / bn;
   const int k_blocks = (g.K + kG2BK - 1) / kG2BK;
-  int splits = 1;
-  const int base = g.m_tiles * g.n_tiles * batch;
-  if (g.mode == kG2Raw && base * 2 <= num_sms) {
-    splits = num_sms / base;
-    if (splits > k_blocks / 8) splits = k_blocks / 8 > 0 ? k_blocks / 8 : 1;
-    const int per = (k_blocks + splits - 1) / splits;
-    splits = (k_blocks + per - 1) / per;
-  }
+  // split-K only with a partition that does not depend on the batch shape (`g.splits` fixed by the caller): a candidate's numbers
+  // must not move with the batch it arrives in
+  int splits = g.part && g.splits > 1 ? g.splits : 1;
+  if (splits > k_blocks) splits = k_blocks;
   g.splits = splits;
-  if (splits > 1) {
-    for (int b = 0; b < batch; ++b) DAN_CUDA_TRY(cudaMemsetAsync(g.out + (long)b * g.out_batch_stride, 0, (size_t)g.M * g.ldo * 4, st));
-  }
   CUtensorMap ma, mb;
   int rc;
   if ((rc = g2_make_map(&ma, A.base, (uint64_t)g.K, (uint64_t)A.rows, (uint64_t)batch, (uint64_t)A.row_stride_bytes, (uint64_t)A.batch_stride_bytes, 128))) return rc;
   if ((rc = g2_make_map(&mb, B.base, (uint64_t)g.K, (uint64_t)B.rows, (uint64_t)batch, (uint64_t)B.row_stride_bytes, (uint64_t)B.batch_stride_bytes, (uint32_t)bn))) return rc;
-  return bn == 64 ? g2_launch<64>(ma, mb, g, st) : g2_launch<32>(ma, mb, g, st);
+  if ((rc = bn == 64 ? g2_launch<64>(ma, mb, g, st) : g2_launch<32>(ma, mb, g, st))) return rc;
+  if (splits > 1) {
+    const long total = (long)batch * g.M * g.N;
+    splitk_reduce_kernel<<<(int)((total + 255) / 256 < 1184 ? (total + 255) / 256 : 1184), 256, 0, st>>>(g.part, splits, batch, g.M, g.N, g.out, g.out_batch_stride, g.ldo);
+    dan_count_launch();
+    DAN_CUDA_TRY(cudaGetLastError());
+  }
+  return DAN_OK;
 }
 
 }  // namespace

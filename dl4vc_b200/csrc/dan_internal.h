@@ -131,3 +131,11 @@ int dan_bf16_encode_reference_order(dan_model* m, const DevInputs& in, int batch
 int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st);
 void dan_bf16_free(dan_model* m);
 int dan_bf16_supported(const dan_model* m);
+
+// training path (dan_train.cu)
+int dan_train_supported(const dan_model* m);
+size_t dan_train_tape_bytes_impl(const dan_model* m, int batch);
+int dan_train_forward_impl(dan_model* m, const dan_weights* w, const DevInputs& in, const uint8_t* removed, int batch, float dropout_p, uint64_t seed,
+                           float* heads_out, void* tape, size_t tape_bytes, cudaStream_t st);
+int dan_backward_impl(dan_model* m, const dan_weights* w, const DevInputs& in, const uint8_t* removed, int batch, float dropout_p, uint64_t seed,
+                      const float* dheads, const float* heads_out, const dan_weights* grads, void* tape, size_t tape_bytes, cudaStream_t st);

@@ -18,11 +18,13 @@ struct EncodeParams {
   int D, Cin, CinPad;
   int use_q, use_s, use_m;
   RowGeom g;
+  const uint8_t* removed;   // optional [candidate][R]: reads replaced by the empty-read encoding (training augmentation, model.py:633-716)
 };
 
 struct EncodeSmem {
   uint8_t* reads; uint8_t* q; uint8_t* st; uint8_t* ref; uint8_t* rm; uint8_t* vm; uint8_t* agreeR; uint8_t* agreeV;
   float* emb;
+  const uint8_t* removed;   // this candidate's row of EncodeParams::removed, or null
 };
 
 __host__ __device__ inline size_t encode_smem_bytes(int P, int R, int D) {
@@ -59,6 +61,7 @@ __device__ inline EncodeSmem encode_stage(const EncodeParams& p, long cand, unsi
   stage_bytes(s.rm, p.in.ref_masks ? p.in.ref_masks + cand * P : nullptr, P, p.use_m && p.in.ref_masks);
   stage_bytes(s.vm, p.in.var_masks ? p.in.var_masks + cand * P : nullptr, P, p.use_m && p.in.var_masks);
   for (int i = threadIdx.x; i < DAN_VOCAB * p.D; i += blockDim.x) s.emb[i] = p.emb[i];
+  s.removed = p.removed ? p.removed + cand * R : nullptr;
   __syncthreads();
   // agreement of read r with the ref / var proposal: every masked column must carry exactly the mask token
   // (integer compare; model.py:592-593 and :607-608 — unmasked columns compare 0 == 0 and always agree)
@@ -79,6 +82,11 @@ __device__ inline EncodeSmem encode_stage(const EncodeParams& p, long cand, unsi
 // value of input channel c at (position pp, read r); channel order = torch.cat order of the reference
 __device__ inline float encode_channel(const EncodeParams& p, const EncodeSmem& s, int c, int pp, int r) {
   const int D = p.D, R = p.g.R;
+  if (s.removed && s.removed[r]) {      // the row of an empty read: pad embedding + reference, every other channel zero (model.py:519-568)
+    if (c < D) return s.emb[c] + __ldg(p.pe + pp * D + c);
+    if (c < 2 * D) return s.emb[s.ref[pp] * D + (c - D)] + __ldg(p.pe + pp * D + (c - D));
+    return 0.f;
+  }
   if (c < D) return s.emb[s.reads[pp * R + r] * D + c] + __ldg(p.pe + pp * D + c);
   if (c < 2 * D) return s.emb[s.ref[pp] * D + (c - D)] + __ldg(p.pe + pp * D + (c - D));
   c -= 2 * D;

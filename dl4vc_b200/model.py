@@ -60,6 +60,26 @@ class _DeviceState:
         self.workspace = {}
 
 
+class _DanTrainFunction(torch.autograd.Function):
+    """Training-mode forward / backward through dan_train_forward / dan_backward (include/dan_b200.h). The parameter tensors are
+    inputs of the Function, so autograd routes the kernel-computed gradients to them (and through nn.DataParallel's broadcast)."""
+
+    @staticmethod
+    def forward(ctx, module, u8, removed, dropout_p, seed, *params):
+        heads, tape = module._train_forward_native(u8, removed, dropout_p, seed)
+        ctx.module, ctx.u8, ctx.removed, ctx.dropout_p, ctx.seed, ctx.tape = module, u8, removed, dropout_p, seed, tape
+        ctx.save_for_backward(heads)
+        ctx.param_shapes = [None if p is None else tuple(p.shape) for p in params]
+        return heads
+
+    @staticmethod
+    def backward(ctx, dheads):
+        (heads,) = ctx.saved_tensors
+        grads = ctx.module._backward_native(ctx.u8, ctx.removed, ctx.dropout_p, ctx.seed, dheads.contiguous().float(), heads, ctx.tape)
+        ctx.tape = None
+        return (None, None, None, None, None, *grads)
+
+
 class Basic2DNet(nn.Module):
     def __init__(self, target_size, layer_sizes=[1024, 256], pre_conv_dropout=0.1, hidden_dropout=0.1,
                  embed_dim=20, pos_embeddings=True, init_conv_channels=CONV_CHANNELS, final_conv_channels=CONV_CHANNELS,
@@ -267,6 +287,11 @@ class Basic2DNet(nn.Module):
         return dev
 
     def _fingerprint(self):
+        """Identity + version of every parameter / buffer of the module that OWNS them. nn.DataParallel replicas (main.py:117) hold
+        freshly broadcast copies whose data_ptr / _version say nothing about the values, so a replica uses the fingerprint its owner
+        took when the replica was made (_replicate_for_data_parallel runs on the owner at every forward)."""
+        if not self.__dict__.get("_native_owner", True):
+            return self._owner_fingerprint
         return tuple((t.data_ptr(), t._version) for t in chain(self.parameters(), self.buffers()))
 
     def _state(self, dev: torch.device) -> _DeviceState:
@@ -349,8 +374,8 @@ class Basic2DNet(nn.Module):
     def forward_heads(self, reads, ref, q_scores=None, strands=None, ref_masks=None, var_masks=None):
         """(B,27) fp32 head matrix [xbinary|xVT|sigmoid(xAF)|leaky_relu(xCov)|xVB|xVR] straight from the kernels."""
         if self.training:
-            raise NotImplementedError("dl4vc_b200.Basic2DNet: training-mode forward (dropout, batch statistics, autograd) is "
-                                      "not implemented yet; call .eval() (trainer.py:476)")
+            raise RuntimeError("forward_heads is the eval-mode path (running BatchNorm statistics, no dropout): call .eval() (trainer.py:476) "
+                               "or forward_train_heads / forward() under autograd for training")
         dev = self._device()
         lib = _lib.load_library()
         with torch.cuda.device(dev):
@@ -381,7 +406,7 @@ class Basic2DNet(nn.Module):
         The library cuts the batch into chunks and overlaps the H2D copy of chunk k+1 (side stream) with the kernels of chunk k
         (dan_forward_host). Asynchronous on the current stream: synchronize it before reading `out`."""
         if self.training:
-            raise NotImplementedError("dl4vc_b200.Basic2DNet: training-mode forward is not implemented; call .eval()")
+            raise RuntimeError("forward_heads_host is the eval-mode path: call .eval() first")
         dev = self._device()
         lib = _lib.load_library()
 
@@ -417,14 +442,159 @@ class Basic2DNet(nn.Module):
             self.last_launch_count = lib.dan_last_launch_count()
         return out
 
+    # ---- training (dan_train_forward / dan_backward) -------------------------------------------------------
+    def _train_params(self):
+        """(name, tensor or None) of every tensor that receives a gradient from the kernels, in the order of DanWeightsC."""
+        cfg = self.dan_config
+        out = [("embeddings", self.embeddings.weight)]
+        res_i = 0
+        for l in range(cfg.total_conv_layers):
+            conv, bn = self.conv1D_layers[l], self.bn1D_layers[l]
+            out += [(f"conv_w.{l}", conv.weight), (f"conv_b.{l}", conv.bias)]
+            out += [(f"bn_w.{l}", bn.weight if cfg.use_batchnorm else None), (f"bn_b.{l}", bn.bias if cfg.use_batchnorm else None)]
+            if self.is_residual_layer[l]:
+                rc = self.residual_conv_layers[res_i]; res_i += 1
+                out += [(f"res_w.{l}", rc.weight), (f"res_b.{l}", rc.bias)]
+            if cfg.highway:
+                out += [(f"bott_w.{l}", self.conv1D_bottleneck_layers[l].weight), (f"bott_b.{l}", self.conv1D_bottleneck_layers[l].bias),
+                        (f"comp_w.{l}", self.conv1D_compression_layers[l].weight), (f"comp_b.{l}", self.conv1D_compression_layers[l].bias)]
+        for i, idx in enumerate(cfg.fc_indices):
+            out += [(f"fc_w.{i}", self.conv2hidden[idx].weight), (f"fc_b.{i}", self.conv2hidden[idx].bias)]
+        for n in HEAD_NAMES:
+            out += [(f"head_w.{n}", getattr(self, n).weight), (f"head_b.{n}", getattr(self, n).bias)]
+        return out
+
+    def _weights_struct(self, tensors: dict, dev, keep: list):
+        """name -> tensor (layout of _train_params, heads concatenated as head_w / head_b) into a DanWeightsC of device pointers."""
+        w = _lib.DanWeightsC()
+
+        def ptr(t):
+            if t is None:
+                return None
+            t = t.detach()
+            if t.device != dev or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(device=dev, dtype=torch.float32).contiguous()
+            keep.append(t)
+            return t.data_ptr()
+
+        for name, t in tensors.items():
+            field, _, idx = name.partition(".")
+            if field in ("embeddings", "head_w", "head_b"):
+                setattr(w, field, ptr(t))
+            else:
+                getattr(w, field)[int(idx)] = ptr(t)
+        return w
+
+    def _u8_inputs(self, reads, ref, q_scores, strands, ref_masks, var_masks, dev):
+        P, R = self.single_read_len, self.num_single_reads
+        if tuple(reads.shape[1:]) != (P, R):
+            raise RuntimeError(f"reads must be (batch, {P}, {R}) [batch, position, read] (dataset.py:672-680), got {tuple(reads.shape)}")
+        return (self._u8(reads, dev), self._u8(q_scores, dev) if self.use_q_scores else None, self._u8(strands, dev) if self.use_strands else None,
+                self._u8(ref, dev), self._u8(ref_masks, dev) if self.use_reads_ref_var_mask else None,
+                self._u8(var_masks, dev) if self.use_reads_ref_var_mask else None)
+
+    def _choose_removed(self, u8, rm_non_var_reads, rm_var_reads):
+        """Read-removal augmentation (model.py:633-716): per round, at most one read per candidate that agrees with the variant proposal
+        (rm_var_reads) / covers the centre column without agreeing (rm_non_var_reads) is replaced by the empty-read encoding. The
+        reference draws with torch.randperm; here: a uniform draw per candidate among its eligible reads. Returns (B, R) uint8 or None."""
+        if not (rm_non_var_reads or rm_var_reads) or not self.use_reads_ref_var_mask:
+            return None
+        reads, var_masks = u8[0], u8[5]
+        nz = (var_masks != 0).unsqueeze(2)
+        agree = ((reads * nz) == var_masks.unsqueeze(2)).all(dim=1)                       # (B, R), model.py:607-608
+        has_read = reads[:, READ_MIDPOINT, :] != 0
+        removed = torch.zeros_like(agree)
+        for eligible, rounds in ((agree, int(rm_var_reads)), (has_read & ~agree, int(rm_non_var_reads))):
+            for _ in range(rounds):
+                score = torch.rand(eligible.shape, device=eligible.device).masked_fill(~eligible, -1.0)
+                pick = score.argmax(dim=1)
+                hit = eligible.any(dim=1)
+                removed[torch.arange(len(pick), device=pick.device)[hit], pick[hit]] = True
+        return removed.to(torch.uint8).contiguous()
+
+    def _train_forward_native(self, u8, removed, dropout_p, seed):
+        dev = self._device()
+        lib = _lib.load_library()
+        with torch.cuda.device(dev):
+            st = self._state(dev)                     # packs the fp32 store from the current parameter values
+            B = int(u8[0].shape[0])
+            need = lib.dan_train_tape_bytes(st.handle, B)
+            if need == 0:
+                raise NotImplementedError("the training kernels do not cover this configuration")
+            tape = torch.empty(int(need), dtype=torch.uint8, device=dev)
+            keep = []
+            names = dict(self._train_params())
+            heads_w = torch.cat([getattr(self, n).weight.detach() for n in HEAD_NAMES], dim=0)
+            tensors = {k: v for k, v in names.items() if not k.startswith("head_")}
+            tensors["head_w"] = heads_w
+            w = self._weights_struct(tensors, dev, keep)
+            for l in range(self.dan_config.total_conv_layers):       # running statistics: updated in place by the kernels
+                bn = self.bn1D_layers[l]
+                w.bn_mean[l] = bn.running_mean.data_ptr(); w.bn_var[l] = bn.running_var.data_ptr()
+            out = torch.empty((B, _lib.NUM_HEAD_OUTPUTS), dtype=torch.float32, device=dev)
+            p = lambda t: None if t is None else t.data_ptr()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.dan_train_forward(st.handle, _lib.C.byref(w), p(u8[0]), p(u8[1]), p(u8[2]), p(u8[3]), p(u8[4]), p(u8[5]), p(removed), B,
+                                             float(dropout_p), int(seed), out.data_ptr(), tape.data_ptr(), tape.numel(), stream), "dan_train_forward")
+            if self.dan_config.use_batchnorm:
+                for bn in self.bn1D_layers:              # like nn.BatchNorm2d in training mode; also tells the packed-weight cache that buffers moved
+                    bn.num_batches_tracked += 1
+        return out, tape
+
+    def _backward_native(self, u8, removed, dropout_p, seed, dheads, heads, tape):
+        dev = self._device()
+        lib = _lib.load_library()
+        with torch.cuda.device(dev):
+            st = self._native[dev.index]
+            B = int(u8[0].shape[0])
+            keep = []
+            params = self._train_params()
+            tensors = {k: v for k, v in params if not k.startswith("head_")}
+            tensors["head_w"] = torch.cat([getattr(self, n).weight.detach() for n in HEAD_NAMES], dim=0)
+            w = self._weights_struct(tensors, dev, keep)
+            for l in range(self.dan_config.total_conv_layers):
+                bn = self.bn1D_layers[l]
+                w.bn_mean[l] = bn.running_mean.data_ptr(); w.bn_var[l] = bn.running_var.data_ptr()
+            grads = {k: (None if v is None else torch.empty_like(v, dtype=torch.float32, device=dev, memory_format=torch.contiguous_format))
+                     for k, v in params if not k.startswith("head_")}
+            hidden = self.final_hidden_size
+            grads["head_w"] = torch.empty((_lib.NUM_HEAD_OUTPUTS, hidden), dtype=torch.float32, device=dev)
+            grads["head_b"] = torch.empty((_lib.NUM_HEAD_OUTPUTS,), dtype=torch.float32, device=dev)
+            gw = self._weights_struct(grads, dev, keep)
+            p = lambda t: None if t is None else t.data_ptr()
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            _lib.check(lib.dan_backward(st.handle, _lib.C.byref(w), p(u8[0]), p(u8[1]), p(u8[2]), p(u8[3]), p(u8[4]), p(u8[5]), p(removed), B,
+                                        float(dropout_p), int(seed), dheads.data_ptr(), heads.data_ptr(), _lib.C.byref(gw), tape.data_ptr(), tape.numel(),
+                                        stream), "dan_backward")
+            out, row = [], 0
+            for name, t in params:
+                if name.startswith("head_w."):
+                    n = t.shape[0]; out.append(grads["head_w"][row:row + n]); continue
+                if name.startswith("head_b."):
+                    n = t.shape[0]; out.append(grads["head_b"][row:row + n]); row += n; continue
+                out.append(grads[name])
+        return out
+
+    def forward_train_heads(self, reads, ref, q_scores=None, strands=None, ref_masks=None, var_masks=None, rm_non_var_reads=0, rm_var_reads=0):
+        """(B,27) head matrix of the training-mode forward, autograd-connected to the parameters through the native backward."""
+        dev = self._device()
+        u8 = self._u8_inputs(reads, ref, q_scores, strands, ref_masks, var_masks, dev)
+        removed = self._choose_removed(u8, rm_non_var_reads, rm_var_reads)
+        seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        params = [t for _, t in self._train_params()]
+        return _DanTrainFunction.apply(self, u8, removed, float(self.dropout), seed, *params)
+
     def forward(self, reads, ref, q_scores, strands, binary_trust_vector,
                 af_scores, ref_bases, var_bases, ref_masks, var_masks,
                 rm_non_var_reads=0, rm_var_reads=0, debug=False):
-        if rm_non_var_reads or rm_var_reads:
-            raise NotImplementedError("read-removal augmentation (model.py:633-716) is training-only and not accelerated")
         if len(self.conv_1d_pool_layers) > 0 and not (self.conv_1d_pool_append or self.conv_1d_pool_add):
             assert False, "Require conv_1d_pool_append or conv_1d_pool_add for appending intermediateAvePool1D"   # model.py:744
-        h = self.forward_heads(reads, ref, q_scores, strands, ref_masks, var_masks)
+        if self.training and torch.is_grad_enabled():
+            h = self.forward_train_heads(reads, ref, q_scores, strands, ref_masks, var_masks, rm_non_var_reads, rm_var_reads)
+        else:
+            if rm_non_var_reads or rm_var_reads:
+                raise NotImplementedError("read-removal augmentation (model.py:633-716) belongs to the training-mode forward")
+            h = self.forward_heads(reads, ref, q_scores, strands, ref_masks, var_masks)
         xbinary, xVT, xAF, xCov, xVB, xVR = h[:, 0:2], h[:, 2:5], h[:, 5:6], h[:, 6:7], h[:, 7:17], h[:, 17:27]
         return (xbinary, xVT, xAF, xCov, xVB, xVR, [], [],
                 self.bin_output_weights, self.vt_output_weights, None, None, None, None)
@@ -465,6 +635,7 @@ class Basic2DNet(nn.Module):
     def _replicate_for_data_parallel(self):
         replica = super()._replicate_for_data_parallel()
         replica._native_owner = False        # nn.DataParallel replicas (main.py:117) share, but never free, the handles
+        replica._owner_fingerprint = self._fingerprint()
         return replica
 
     def __getstate__(self):

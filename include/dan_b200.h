@@ -162,6 +162,30 @@ enum { DAN_MASK_OK = 0, DAN_MASK_E_ALLELE_CHAR = 1,   /* character outside base_
 int dan_make_mask_vectors(const char* const* ref_alleles, const char* const* var_alleles, const uint8_t* references, int n,
                           uint8_t* ref_masks, uint8_t* var_masks, int32_t* status);
 
+/* ---- training (BASELINE configs[4]) -----------------------------------------------------------------------------------------
+ * Replaces Basic2DNet.forward with self.training set and the autograd graph PyTorch builds behind it (dl4vc/model.py:434-961 called
+ * from dl4vc/trainer.py:213-217; backward at trainer.py:426-439). fp32 on the CUDA-core kernels of the accuracy path.
+ *
+ * dan_train_forward: like dan_forward (DEVICE uint8 inputs, batch*27 fp32 outputs) but BatchNorm normalises with the statistics of
+ * this batch and updates the running statistics IN PLACE through params->bn_mean / bn_var (momentum 0.1, unbiased variance), the
+ * three Dropout modules of the FC trunk use a counter-based mask derived from (seed, element index) with probability dropout_p, and
+ * reads flagged in `removed` (batch*num_reads bytes, may be NULL) are replaced by the empty-read encoding (the read-removal
+ * augmentation of model.py:633-716; the caller picks the reads like the reference's randperm does). `params` are the live fp32
+ * parameter tensors (state_dict layout); dan_model_load_weights must have been called on the same values. Everything the backward
+ * pass needs stays in `tape` (dan_train_tape_bytes).
+ *
+ * dan_backward: d(loss)/d(heads) (batch*27, w.r.t. the returned, activated outputs) -> gradient of every parameter tensor, written
+ * (not accumulated) into the tensors `grads` points to (same layout as `params`; head_w / head_b as the 27-row concatenation;
+ * entries may be NULL to skip embeddings). Must follow dan_train_forward on the same tape, inputs, seed and dropout_p. */
+size_t dan_train_tape_bytes(const dan_model* m, int batch);
+int dan_train_forward(dan_model* m, const dan_weights* params, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
+                      const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks, const uint8_t* removed, int batch,
+                      float dropout_p, uint64_t seed, float* heads_out, void* tape, size_t tape_bytes, void* stream);
+int dan_backward(dan_model* m, const dan_weights* params, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
+                 const uint8_t* ref, const uint8_t* ref_masks, const uint8_t* var_masks, const uint8_t* removed, int batch,
+                 float dropout_p, uint64_t seed, const float* dheads, const float* heads_out, const dan_weights* grads,
+                 void* tape, size_t tape_bytes, void* stream);
+
 /* Test hook for the bit-exact integer/encoding work (dl4vc/model.py:450-627,719): writes the conv-1 input in the
  * reference's logical order (batch, Cin, num_reads, read_len) fp32, DEVICE pointer. */
 int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,
