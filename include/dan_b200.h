@@ -186,6 +186,29 @@ int dan_backward(dan_model* m, const dan_weights* params, const uint8_t* reads, 
                  float dropout_p, uint64_t seed, const float* dheads, const float* heads_out, const dan_weights* grads,
                  void* tape, size_t tape_bytes, void* stream);
 
+/* Replaces the trainer's per-step loss block (dl4vc/trainer.py:252-255,309-313,426-427; dl4vc/objectives.py:49-112) and the host round
+ * trips around it (trainer.py:258,263,267) with one kernel: heads (batch*27 fp32 as returned by dan_train_forward) + targets (all DEVICE
+ * pointers: label<=1, var_type, allele_freq, coverage * 0.01, var_base_enum, var_ref_enum, per-example weight or NULL) ->
+ *   losses_out[8] = { binary, genotype, allele-frequency, coverage, variant-base, reference-base, weighted total, number of close
+ *                     (easy) examples }, dheads_out = d(total)/d(heads) (batch*27, ready for dan_backward), close_vt / close_bin =
+ *   the "well classified" flags of objectives.py:110-111 (batch bytes each). dan_close_table_update scatters flags into the per-example
+ *   table the next epoch's sampler reads (dl4vc/dataset.py:480,719-732) without leaving the device. */
+typedef struct dan_loss_config {
+  float label_smoothing;      /* arguments.py:33 (train_variant_caller.sh: 0.001) */
+  float close_match_window;   /* arguments.py:35 (2.0) */
+  float focal_gamma;          /* arguments.py:37 (0.2) */
+  float focal_alpha;          /* arguments.py:39 (1.0) */
+  float fp_train_weight;      /* pos_weight[0] of both classification losses, trainer.py:84-96 */
+  float binary_weight;        /* trainer.py:426 */
+  float aux_weight;           /* args.auxillary_loss_weight */
+  float aux_allele_weight;    /* args.auxillary_loss_allele_weight */
+  float aux_bases_weight;     /* args.auxillary_loss_bases_weight */
+} dan_loss_config;
+int dan_losses(const float* heads, int batch, const int32_t* target_binary, const int32_t* target_var_type, const float* target_allele_freq,
+               const float* target_coverage, const int32_t* target_var_base, const int32_t* target_ref_base, const float* example_weight,
+               const dan_loss_config* cfg, float* losses_out, float* dheads_out, uint8_t* close_vt, uint8_t* close_bin, void* stream);
+int dan_close_table_update(uint8_t* table, int64_t table_len, const int64_t* idx, const uint8_t* flags, int batch, void* stream);
+
 /* Test hook for the bit-exact integer/encoding work (dl4vc/model.py:450-627,719): writes the conv-1 input in the
  * reference's logical order (batch, Cin, num_reads, read_len) fp32, DEVICE pointer. */
 int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,

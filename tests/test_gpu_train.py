@@ -91,3 +91,28 @@ def test_training_step_with_dropout_and_read_removal_runs_and_is_reproducible():
     assert not np.array_equal(a[0], c[0])
     assert not np.array_equal(a[0], d[0])
     assert np.isfinite(a[1]).all() and np.abs(a[1]).max() > 0 and np.all(a[2][0] == 0)      # padding_idx row gets no gradient
+
+
+def test_device_losses_match_reference_loss_block():
+    """dan_losses (one kernel: focal soft-BCE x2, allele-frequency BCE, coverage MSE, two weighted cross entropies, weighted total, gradient
+    w.r.t. the model outputs, close flags) against the REAL reference's objectives.py + trainer.py loss lines and torch autograd
+    (tests/golden/losses.npz, oracle/make_loss_goldens.py)."""
+    import os
+    from conftest import GOLDEN_DIR
+    from dl4vc_b200.losses import LossConfig, fused_losses, update_close_table
+    g = np.load(os.path.join(GOLDEN_DIR, "losses.npz"))
+    cfg = LossConfig(**{k[4:]: float(g[k]) for k in g.files if k.startswith("cfg_")})
+    heads = torch.tensor(g["heads"], device="cuda", requires_grad=True)
+    t = lambda k: torch.from_numpy(g[k]).cuda()
+    total, comps, close_vt, close_bin = fused_losses(heads, t("target_binary"), t("target_var_type"), t("target_allele_freq"), t("target_coverage"),
+                                                     t("target_var_base"), t("target_ref_base"), t("example_weight"), cfg)
+    (total * 1.0).backward()
+    np.testing.assert_allclose(comps.cpu().numpy(), g["losses"], rtol=2e-5, atol=1e-6)
+    assert abs(total.item() - g["losses"][6]) < 2e-5 * abs(g["losses"][6])
+    want = g["dheads"]
+    assert np.abs(heads.grad.cpu().numpy() - want).max() < 2e-5 * np.abs(want).max()
+    assert np.array_equal(close_vt.cpu().numpy(), g["close_vt"]) and np.array_equal(close_bin.cpu().numpy(), g["close_bin"])
+    table = torch.zeros(200, dtype=torch.uint8, device="cuda")
+    idx = torch.arange(len(want), device="cuda") * 2
+    update_close_table(table, idx, close_vt)
+    assert int(table.sum()) == int(g["close_vt"].sum()) and bool(table[::2][: len(want)].cpu().eq(torch.from_numpy(g["close_vt"])).all())
