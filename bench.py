@@ -48,6 +48,25 @@ def load_peaks():
     return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm_gbs": 6650.0, "source": "fallback"}
 
 
+def stack_kernel_traffic():
+    """DRAM bytes (read + write) of the conv-stack kernel per launch and per candidate, from the committed `ncu --set full` capture of a
+    148-candidate pass (profiles/r02_stack_kernel_ncu_full_summary.csv: one column per segment launch)."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r02_stack_kernel_ncu_full_summary.csv")
+    if not os.path.exists(path):
+        return None
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total, launches, cands = 0.0, 0, 148
+    with open(path) as f:
+        for row in csv.reader(f):
+            if row and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                vals = [float(v) * scale[row[1]] for v in row[2:] if v]
+                total += sum(vals); launches = len(vals)
+    if not launches:
+        return None
+    return {"per_launch": total / launches, "per_candidate": total / cands, "source": "ncu --set full, profiles/r02_stack_kernel_ncu_full_summary.csv"}
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock and throttle reasons with NVML while the timed region runs."""
 
@@ -175,6 +194,90 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def fp32_block(model, sample, dev, cfg, clocks, batch=592, steps=3):
+    """BASELINE configs[1]: the fp32 path (logits within 1e-4 of the reference, tests/test_gpu_parity.py) on 4 full passes, resident and
+    through the host-buffer call. CUDA-core FFMA: quoted against the FMA peak of the part at the sampled maximum SM clock."""
+    import numpy as np
+    import torch
+    from dl4vc_b200 import _lib
+    reps = (batch + len(sample) - 1) // len(sample)
+    host = [torch.from_numpy(np.ascontiguousarray(np.concatenate([a] * reps, axis=0)[:batch])).pin_memory() for a in sample.arrays()]
+    h_r, h_q, h_s, h_ref, h_rm, h_vm = host
+    d_r, d_q, d_s, d_ref, d_rm, d_vm = [t.to(dev) for t in host]
+    model.set_precision("fp32")
+    out_host = torch.empty((batch, _lib.NUM_HEAD_OUTPUTS), dtype=torch.float32).pin_memory()
+    res = {}
+    for name, fn in (("value", lambda: model.forward_heads(d_r, d_ref, d_q, d_s, d_rm, d_vm)),
+                     ("e2e", lambda: model.forward_heads_host(h_r, h_ref, h_q, h_s, h_rm, h_vm, out=out_host))):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        res[name] = batch * steps / (e0.elapsed_time(e1) * 1e-3)
+    model.set_precision("bf16")
+    fma_peak = 148 * 128 * 2 * (clocks.get("sm_max_mhz") or 1965) * 1e6 / 1e12
+    ach = res["value"] * 2 * cfg.macs_per_candidate() / 1e12
+    return {"value": res["value"], "e2e": res["e2e"], "unit": UNIT, "candidates_per_step": batch, "steps": steps, "dtype": "f32",
+            "tolerance": "logits within 1e-4 relative of the reference (tests/test_gpu_parity.py)",
+            "roofline": {"bound": "fp32_fma (CUDA cores)", "achieved": ach, "peak": fma_peak, "unit": "TFLOP/s", "frac": ach / fma_peak,
+                         "peak_source": "nominal: 148 SMs x 128 FMA lanes x 2 x sm_max_mhz"}}
+
+
+def train_step_block(cfg, sd, dev, dist, world, rank, timed, batch=32, steps=3):
+    """BASELINE configs[4]: one data-parallel training step per rank = training-mode forward (batch-statistics BatchNorm, dropout 0.1, read
+    removal) -> device loss block (dan_losses) -> native backward -> bucketed gradient all-reduce over NCCL -> grad clip 1.0 -> Adam, with the
+    close-example flags scattered into the device-resident table (easy-example down-sampling input). fp32 kernels; `value` counts the
+    candidates of all ranks."""
+    import numpy as np
+    import torch
+    from dl4vc_b200.factory import build_model
+    from dl4vc_b200.losses import fused_losses, update_close_table
+    from dl4vc_b200.synth import make_pileups
+    from dl4vc_b200.train_dp import GradientAllReducer
+    model = build_model(cfg, sd, device=dev, precision="fp32").train()
+    opt = torch.optim.Adam(model.parameters(), lr=2e-4)            # main.py:116, train_variant_caller.sh
+    reducer = GradientAllReducer(model)
+    b = make_pileups(batch, seed=4242 + rank, coverage="poisson")
+    d = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in b.arrays()]
+    vt = torch.from_numpy(np.rint(b.var_fraction * 2).astype(np.int64)).to(dev)
+    tb = (vt > 0).long()
+    af = torch.from_numpy(b.var_fraction.astype(np.float32)).to(dev)
+    cov = torch.from_numpy((b.num_reads * 0.01).astype(np.float32)).to(dev)
+    vb = torch.from_numpy(b.var_masks[:, 100].astype(np.int64)).to(dev); vr = torch.from_numpy(b.ref_masks[:, 100].astype(np.int64)).to(dev)
+    table = torch.zeros(1 << 20, dtype=torch.uint8, device=dev)
+    idx = torch.arange(batch, device=dev) + rank * batch
+    state = {}
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        heads = model.forward_train_heads(d[0], d[3], d[1], d[2], d[4], d[5], rm_non_var_reads=0, rm_var_reads=1)
+        total, comps, close_vt, _ = fused_losses(heads, tb, vt, af, cov, vb, vr)
+        total.backward()
+        reducer()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1.0)        # train_variant_caller.sh:104
+        opt.step()
+        update_close_table(table, idx, close_vt)
+        state["loss"] = comps
+
+    for _ in range(2):
+        step()
+    ms = timed(step, steps)
+    grad_bytes = sum(p.numel() for p in model.parameters() if p.requires_grad) * 4
+    loss = [round(float(x), 4) for x in state["loss"].cpu()]
+    del model, opt
+    torch.cuda.empty_cache()
+    return {"value": batch * world * steps / (ms * 1e-3), "unit": "candidates/s (training step)", "batch_per_gpu": batch, "steps": steps, "ms_per_step": ms / steps,
+            "dtype": "f32", "collective": None if world == 1 else f"NCCL all-reduce (sum / {world}) of {grad_bytes / 1e6:.0f} MB fp32 gradients per step in 2 buckets "
+                                                                    "(FC trunk + heads first, on a side stream), BatchNorm statistics per GPU",
+            "step": "train forward + dan_losses + dan_backward + gradient all-reduce + clip_grad_norm 1.0 + Adam + close-table scatter",
+            "last_losses[bin,vt,af,cov,vb,vr,total,n_close]": loss}
+
+
 def run_b200(args):
     import numpy as np
     import torch
@@ -277,6 +380,7 @@ def run_b200(args):
     lib.dan_profile_enable(0)
     clocks = sampler.stop()
 
+    train_block = None if args.no_train else train_step_block(cfg, sd, dev, dist, world, rank, timed)
     total_cands = B * world * args.steps
     value = total_cands / (ms * 1e-3)
     e2e_value = total_cands / (ms_e2e * 1e-3)
@@ -286,6 +390,7 @@ def run_b200(args):
         return 0
 
     peaks = load_peaks()
+    traffic = stack_kernel_traffic()
     R, P, Cc = cfg.num_reads, cfg.read_len, cfg.channels
     # conv-stack class = conv(1x3) + residual 1x1 + bottleneck 1x1 MACs; compression/FC/heads run in the GEMM class
     macs_conv_stack = 0
@@ -310,10 +415,9 @@ def run_b200(args):
     roofline = {
         "bound": "tensor", "kernel": "dan_stack_kernel (conv stack class)", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
         "frac": (achieved / peak) if peak else None,
-        # dram__bytes_read.sum + dram__bytes_write.sum of dan_stack_kernel from the committed `ncu --set full` capture
-        # (profiles/r01e_stack_kernel_ncu_full_summary.csv: 1.384 GB + 2.500 GB for the two segment launches of a 148-candidate pass
-        # = 26.24 MB per candidate), averaged per launch like `achieved`
-        "traffic": 26.24e6 * B / dom_launches, "traffic_source": "ncu --set full, profiles/r01e (26.2 MB per candidate over both segment launches)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of dan_stack_kernel per launch, read from the committed `ncu --set full` capture
+        "traffic": traffic["per_launch"] if traffic else None, "traffic_per_candidate": traffic["per_candidate"] if traffic else None,
+        "traffic_source": traffic["source"] if traffic else "no committed capture",
         "peak_source": f"{peaks['source']} bf16_tflops_sustained (kernel timed inside a long step); burst {peaks['bf16_burst']}",
         "launches_per_step": dom_launches, "avg_launch_ms": dom_ms_step / dom_launches,
         "share_of_step": dom_ms_step / sum(cls_ms.values()) if sum(cls_ms.values()) > 0 else None,
@@ -342,12 +446,15 @@ def run_b200(args):
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline,
     }
+    line["train"] = train_block
+    if world == 1 and args.precision == "bf16" and not args.no_fp32:
+        line["fp32"] = fp32_block(model, sample, dev, cfg, clocks)
     if world == 1 and not args.no_cpu_baseline:
         cores = os.cpu_count() or 1
-        nb = 64
-        rate, times = cpu_reference_rate(cfg, sd, sample, nb, repeats=2, warmup=1)
+        nb, reps = 64, 10                  # >= 640 timed candidates
+        rate, times = cpu_reference_rate(cfg, sd, sample, nb, repeats=reps, warmup=1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"2 timed batches x {nb} of the same dense PROD candidates (1 warm-up), torch {torch.__version__} "
+                                "sample": f"{reps} timed batches x {nb} = {reps * nb} of the same dense PROD candidates (1 warm-up), torch {torch.__version__} "
                                           f"CPU fp32, oracle/dan_torch_cpu.py = the reference's op sequence; batch times {['%.2f' % t for t in times]} s"}
     print(json.dumps(line), flush=True)
     if dist is not None:
@@ -365,6 +472,8 @@ def main():
     ap.add_argument("--batch", type=int, default=4144, help="candidates per step per GPU (28 passes of 148 candidates)")
     ap.add_argument("--pass-candidates", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fp32", action="store_true", help="skip the fp32 1e-4-parity path block (BASELINE configs[1])")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step block (BASELINE configs[4])")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
