@@ -8,6 +8,9 @@ PinnedBatchFeeder  collates the loader's per-candidate dicts (the schema `dl4vc/
 scores_from_heads  the caller-side post-ops of `trainer.py:611-623`: softmax over xbinary / xVT and the variant score 1 - p0.
 make_mask_vectors  batch proposal-mask decode of the loader (`dataset.py:112-250`) in the C-ABI library, pinned to the reference's outputs.
 scores_on_device   the same post-ops as one CUDA kernel behind the C-ABI (`dan_scores`): 4 floats per candidate leave the GPU.
+RecordFile / decode_records  raw fixed-record pileup file (the reference's HDF5 compound type as a flat np.memmap: h5py is not in the image) and
+                   the batched C decode of `ContextDatasetFromNumpy._get_generator` (`dataset.py:500-680`: row window, sample_single_reads,
+                   parse_vcf, count_variants_from_single_reads, proposal masks) straight into a pinned HostBatch — no per-item Python.
 format_vcf_info    the `BP=..;NV=..;HV=..;OV=..` field `utils.append_vcf_records` splices into VCF column 3 (`utils.py:162-178`).
 """
 from __future__ import annotations
@@ -176,3 +179,74 @@ def splice_vcf_records(vcf_records, bin_score, vt_probs):
         items[2] = txt
         out.append("\t".join(items))
     return out
+
+
+# ---- raw record files + batched decode (dan_decode_records) --------------------------------------------------------------------------
+RECORD_DTYPE = np.dtype([("name", "S16"), ("ref", np.uint8, (5, 201)), ("reads", np.uint16, (5, 201)), ("single_reads", np.uint8, (200, 201)),
+                         ("ref_bases", np.uint8, (201,)), ("num_reads", np.int32), ("label", np.uint8), ("vcfrec", "S128"),
+                         ("q-scores", np.uint8, (200, 201)), ("strand", np.uint8, (200, 201))])      # tools/convert_bam_single_reads.py:694-698
+RECORD_BYTES = 123965
+assert RECORD_DTYPE.itemsize == RECORD_BYTES
+REC_STATUS = {0: "ok", 1: "vcf record has too few columns", 2: "allele letter outside base_enum", 3: "unknown mutation (equal-length non-SNP)",
+              4: "INFO column without AF= / DP=", 5: "proposal masks: the reference raises (not an assertion)"}
+
+
+class RecordFile:
+    """np.memmap over back-to-back records of RECORD_DTYPE (what `hdfile['data']` holds in the reference, dataset.py:501-503)."""
+
+    def __init__(self, path_or_array):
+        if isinstance(path_or_array, np.ndarray):
+            a = path_or_array
+            self.raw = np.ascontiguousarray(a.view(np.uint8).reshape(len(a), -1)) if a.dtype == RECORD_DTYPE else np.ascontiguousarray(a, dtype=np.uint8)
+        else:
+            self.raw = np.memmap(path_or_array, dtype=np.uint8, mode="r").reshape(-1, RECORD_BYTES)
+        assert self.raw.ndim == 2 and self.raw.shape[1] == RECORD_BYTES
+
+    def __len__(self):
+        return self.raw.shape[0]
+
+    def field(self, idx, name):
+        return self.raw[idx].view(RECORD_DTYPE)[0][name]
+
+
+def decode_records(records: RecordFile, indices, batch: HostBatch | None = None, use_q_scores=True, use_strands=True, keep_candidate_af=False, seed=0,
+                   max_reads=100, store_max_reads=200, strict=True):
+    """Decode `indices` of a RecordFile into a (pinned) HostBatch + the per-example scalars the trainer reads (dataset.py:672-680).
+    Returns (batch, scalars dict of numpy arrays incl. `status` / `blacklist`). strict: raise if the reference's loader would."""
+    import ctypes as C
+
+    from . import _lib
+    lib = _lib.load_library()
+
+    class Cfg(C.Structure):
+        _fields_ = [("max_reads", C.c_int32), ("store_max_reads", C.c_int32), ("use_q_scores", C.c_int32), ("use_strands", C.c_int32),
+                    ("keep_candidate_af", C.c_int32), ("seed", C.c_uint64)]
+
+    class Out(C.Structure):
+        _fields_ = [(n, C.c_void_p) for n in ("reads", "q_scores", "strands", "ref", "ref_masks", "var_masks", "label", "num_reads", "is_snp", "var_type",
+                                              "allele_freq", "coverage", "var_base_enum", "var_ref_enum", "blacklist", "status")]
+
+    idx = np.ascontiguousarray(np.asarray(indices, dtype=np.int64))
+    n = len(idx)
+    if n and (idx.min() < 0 or idx.max() >= len(records)):
+        raise IndexError("record index out of range")
+    if batch is None:
+        batch = HostBatch(max(n, 1), num_reads=max_reads)
+    if n > batch.capacity:
+        raise ValueError(f"{n} records > capacity {batch.capacity}")
+    sc = {"label": np.zeros(n, np.uint8), "num_reads": np.zeros(n, np.int32), "is_snp": np.zeros(n, np.uint8), "var_type": np.zeros(n, np.int32),
+          "allele_freq": np.zeros(n, np.float32), "coverage": np.zeros(n, np.int32), "var_base_enum": np.zeros(n, np.int32),
+          "var_ref_enum": np.zeros(n, np.int32), "blacklist": np.zeros(n, np.uint8), "status": np.zeros(n, np.int32)}
+    out = Out(batch.reads.data_ptr(), batch.q.data_ptr(), batch.strands.data_ptr(), batch.ref.data_ptr(), batch.ref_masks.data_ptr(),
+              batch.var_masks.data_ptr(), *[sc[k].ctypes.data for k in ("label", "num_reads", "is_snp", "var_type", "allele_freq", "coverage",
+                                                                         "var_base_enum", "var_ref_enum", "blacklist", "status")])
+    cfg = Cfg(max_reads, store_max_reads, int(use_q_scores), int(use_strands), int(keep_candidate_af), int(seed))
+    lib.dan_decode_records.argtypes = [C.c_void_p, C.c_size_t, C.c_void_p, C.c_int, C.POINTER(Cfg), C.POINTER(Out)]
+    rc = lib.dan_decode_records(records.raw.ctypes.data, RECORD_BYTES, idx.ctypes.data, n, C.byref(cfg), C.byref(out))
+    batch.size = n
+    batch.meta = [(bytes(records.field(int(i), "name")).decode(), bytes(records.field(int(i), "vcfrec")).decode()) for i in idx]
+    if rc < 0 and strict:
+        bad = np.flatnonzero(sc["status"])
+        raise ValueError(f"{len(bad)} records cannot be decoded (the reference loader raises on them): " +
+                         ", ".join(f"#{int(idx[b])}: {REC_STATUS.get(int(sc['status'][b]), '?')}" for b in bad[:5]))
+    return batch, sc

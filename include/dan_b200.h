@@ -209,6 +209,32 @@ int dan_losses(const float* heads, int batch, const int32_t* target_binary, cons
                const dan_loss_config* cfg, float* losses_out, float* dheads_out, uint8_t* close_vt, uint8_t* close_bin, void* stream);
 int dan_close_table_update(uint8_t* table, int64_t table_len, const int64_t* idx, const uint8_t* flags, int batch, void* stream);
 
+/* Replaces the per-item Python loader, ContextDatasetFromNumpy._get_generator (dl4vc/dataset.py:500-680: row window, sample_single_reads
+ * :256-287, parse_vcf utils.py:19-72, count_variants_from_single_reads :340-362, get_read_mask_vectors :112-250) for a batch of record
+ * indices: `records` are raw records of the compound type tools/convert_bam_single_reads.py writes (:694-698; 123 965 bytes, no padding),
+ * `record_stride` bytes apart (np.memmap of that dtype). Outputs are HOST pointers (pin them for dan_forward_host), [candidate][position]
+ * [read] for the three tiles; any output except reads / ref / masks may be NULL. Pileups deeper than max_reads are reduced to a sorted
+ * subset of their rows chosen from (seed, record index) — the reference draws it from the unseeded global numpy generator. status[i] is
+ * DAN_REC_OK or the reason the reference's loader raises on the record; blacklist[i] = 1 where the reference catches the mask assertion
+ * and substitutes all-pad masks. Pure host code. Returns DAN_E_INVALID if any record failed. */
+#define DAN_RECORD_BYTES 123965
+enum { DAN_REC_OK = 0, DAN_REC_E_VCF_FIELDS = 1, DAN_REC_E_ALLELE = 2, DAN_REC_E_UNKNOWN_MUTATION = 3, DAN_REC_E_VCF_INFO = 4, DAN_REC_E_MASK = 5 };
+typedef struct dan_feeder_config {
+  int32_t max_reads;          /* 100 (dataset.py:398) */
+  int32_t store_max_reads;    /* 200 (rows of the stored pileup the window is taken from, dataset.py:410) */
+  int32_t use_q_scores, use_strands;   /* args.model_use_q_scores / model_use_strands: unused tiles stay zero (dataset.py:563,577) */
+  int32_t keep_candidate_af;  /* args.aux_keep_candidate_af (dataset.py:616) */
+  uint64_t seed;
+} dan_feeder_config;
+typedef struct dan_record_batch {
+  uint8_t *reads, *q_scores, *strands;          /* n * 201 * max_reads */
+  uint8_t *ref, *ref_masks, *var_masks;         /* n * 201 */
+  uint8_t* label; int32_t* num_reads; uint8_t* is_snp; int32_t* var_type; float* allele_freq; int32_t* coverage;
+  int32_t *var_base_enum, *var_ref_enum; uint8_t* blacklist; int32_t* status;
+} dan_record_batch;
+int dan_decode_records(const void* records, size_t record_stride, const int64_t* indices, int n, const dan_feeder_config* cfg,
+                       const dan_record_batch* out);
+
 /* Test hook for the bit-exact integer/encoding work (dl4vc/model.py:450-627,719): writes the conv-1 input in the
  * reference's logical order (batch, Cin, num_reads, read_len) fp32, DEVICE pointer. */
 int dan_encode(dan_model* m, const uint8_t* reads, const uint8_t* q_scores, const uint8_t* strands,

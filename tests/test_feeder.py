@@ -99,3 +99,51 @@ def test_mask_vector_decode_matches_reference_goldens():
     good = np.nonzero(ok)[0][:50]
     rm2, vm2, st2 = make_mask_vectors([xs[i] for i in good], [ys[i] for i in good], g["references"][good])
     assert not st2.any() and np.array_equal(rm2, g["ref_masks"][good])
+
+
+def test_decode_records_matches_reference_loader():
+    """dan_decode_records (batched C decode of raw records) against the per-item dicts of the REAL ContextDatasetFromNumpy.__getitem__
+    (tests/golden/feeder.npz, oracle/make_feeder_goldens.py): tiles, reference, proposal masks and every scalar exactly; pileups deeper
+    than 100 reads (sampled with an unseeded np.random.choice in the reference) are checked for the sampling properties."""
+    import os
+    from conftest import GOLDEN_DIR
+    from dl4vc_b200.feeder import RECORD_DTYPE, HostBatch, RecordFile, decode_records
+    g = np.load(os.path.join(GOLDEN_DIR, "feeder.npz"))
+    rf = RecordFile(g["records"])
+    n = len(rf)
+    raised = [str(r) for r in g["raised"]]
+    ok = np.array([r == "" for r in raised])
+    batch, sc = decode_records(rf, np.arange(n), HostBatch(n, pin=False), seed=5, strict=False)
+    assert np.array_equal(sc["status"] != 0, ~ok), "records the reference raises on <-> non-zero status"
+    with pytest.raises(ValueError, match="cannot be decoded"):
+        decode_records(rf, np.arange(n), HostBatch(n, pin=False))
+    depth = sc["num_reads"]
+    shallow = ok & (depth <= 100)
+    deep = ok & (depth > 100)
+    assert shallow.sum() >= 15 and deep.sum() >= 10
+    got = {"reads": batch.reads.numpy(), "q_scores": batch.q.numpy(), "strands": batch.strands.numpy(), "ref": batch.ref.numpy(),
+           "ref_mask": batch.ref_masks.numpy(), "var_mask": batch.var_masks.numpy()}
+    for k, a in got.items():
+        assert np.array_equal(a[shallow], g["out_" + k][shallow]), k
+    for k in ("ref", "ref_mask", "var_mask"):
+        assert np.array_equal(got[k][deep], g["out_" + k][deep]), k
+    for k in ("label", "num_reads", "is_snp", "var_type", "var_base_enum", "var_ref_enum", "blacklist"):
+        assert np.array_equal(sc[k][ok].astype(np.float64), g["s_" + k][ok]), k
+    for k in ("allele_freq", "coverage"):      # depend on the sampled rows: exact for shallow pileups
+        assert np.array_equal(sc[k][shallow].astype(np.float64), g["s_" + k][shallow].astype(np.float32).astype(np.float64)), k
+    assert sc["blacklist"][1] == 1 and not got["ref_mask"][1].any()
+    # deep pileups: 100 columns = a sorted subset of the first num_reads stored rows, the same rows in all three tiles, deterministic in (seed, index)
+    recs = g["records"].view(RECORD_DTYPE).reshape(-1)
+    for i in np.flatnonzero(deep):
+        rows, qrows, srows = recs[i]["single_reads"], recs[i]["q-scores"], recs[i]["strand"]
+        last = -1
+        for j in range(100):
+            col = got["reads"][i][:, j]
+            cands = [r for r in range(last + 1, int(depth[i])) if np.array_equal(rows[r], col) and np.array_equal(qrows[r], got["q_scores"][i][:, j])
+                     and np.array_equal(srows[r], got["strands"][i][:, j])]
+            assert cands, f"record {i}: column {j} is not a later stored row"
+            last = cands[0]
+    again, _ = decode_records(rf, np.arange(n), HostBatch(n, pin=False), seed=5, strict=False)
+    assert np.array_equal(again.reads.numpy(), got["reads"])
+    other, _ = decode_records(rf, np.arange(n), HostBatch(n, pin=False), seed=6, strict=False)
+    assert not np.array_equal(other.reads.numpy()[deep], got["reads"][deep])
