@@ -70,7 +70,10 @@ def build(force: bool = False, verbose: bool = False, defines=(), out: str = OUT
 
 
 if __name__ == "__main__":
-    if "--prof" in sys.argv:
+    if "--define" in sys.argv:      # development: python -m dl4vc_b200.build --define NAME -> libdan_b200_name.so
+        d = sys.argv[sys.argv.index("--define") + 1]
+        print(build(force=True, verbose="-v" in sys.argv, defines=(d,), out=os.path.join(HERE, "libdan_b200_%s.so" % d.lower())))
+    elif "--prof" in sys.argv:
         print(build(force=True, verbose="-v" in sys.argv, defines=("DAN_STK_PROF",), out=os.path.join(HERE, "libdan_b200_prof.so")))
     else:
         print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -622,15 +622,16 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
     const int blocks = ns * (sum_groups_per_cand(m) / 2);
     const int grid = blocks < bw->num_sms ? blocks : bw->num_sms;
 #ifdef DAN_STK_PROF
-    DAN_CUDA_TRY(cudaMalloc(&sp.prof, sizeof(unsigned long long) * 64 * grid));
-    DAN_CUDA_TRY(cudaMemsetAsync(sp.prof, 0, sizeof(unsigned long long) * 64 * grid, st));
+    const size_t prof_words = (size_t)64 * grid + 4 * kStkTraceCap;
+    DAN_CUDA_TRY(cudaMalloc(&sp.prof, sizeof(unsigned long long) * prof_words));
+    DAN_CUDA_TRY(cudaMemsetAsync(sp.prof, 0, sizeof(unsigned long long) * prof_words, st));
 #endif
     { DanProfScope ps(DAN_PROF_CONV_STACK, st); dan_stack_kernel<<<grid, kStkThreads, kStkSmemBytes, st>>>(sp); }
     dan_count_launch();
     DAN_CUDA_TRY(cudaGetLastError());
 #ifdef DAN_STK_PROF
     {   // development build (python -m dl4vc_b200.build --prof): per-role cycle counters, mean over CTAs, one line per launch
-      std::vector<unsigned long long> hbuf(64 * (size_t)grid);
+      std::vector<unsigned long long> hbuf(prof_words);
       DAN_CUDA_TRY(cudaStreamSynchronize(st));
       DAN_CUDA_TRY(cudaMemcpy(hbuf.data(), sp.prof, hbuf.size() * 8, cudaMemcpyDeviceToHost));
       cudaFree(sp.prof);
@@ -646,6 +647,22 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
         const double* e = a + 28 + 14 * sl;
         fprintf(stderr, "[stkprof]   epilogue slot %d: other %.0f wait-bott %.0f bott-epi %.0f wait-acc %.0f main-epi %.0f post-epi %.0f tma: bar %.0f wait0 %.0f issue %.0f | wait-read-out %.0f prepare %.0f arrive %.0f total %.0f\n", sl,
                 e[0] / reads, e[1] / reads, e[2] / reads, e[3] / reads, e[4] / reads, e[5] / reads, e[10] / reads, e[11] / reads, e[6] / reads, e[7] / reads, e[8] / reads, e[12] / reads, e[9] / reads);
+      }
+      // event trace of CTA 0 (reads 10-13 of each slot): one file per segment shape, written once
+      static int dumped[2] = {0, 0};
+      if (!dumped[l > 0]) {
+        dumped[l > 0] = 1;
+        char path[128];
+        snprintf(path, sizeof(path), "gpurun_out/stk_trace_l%d.txt", l + 1);
+        if (FILE* f = fopen(path, "w")) {
+          static const char* role[4] = {"issuer0", "issuer1", "epi0", "epi1"};
+          for (int r = 0; r < 4; ++r)
+            for (int i = 0; i < kStkTraceCap; ++i) {
+              const unsigned long long v = hbuf[(size_t)64 * grid + (size_t)r * kStkTraceCap + i];
+              if (v) fprintf(f, "%s %llu %llu\n", role[r], v >> 48, v & ((1ull << 48) - 1));
+            }
+          fclose(f);
+        }
       }
     }
 #endif

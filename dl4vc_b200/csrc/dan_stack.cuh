@@ -43,8 +43,8 @@ constexpr int kStkN = 208;             // MMA N = positions per read, padded to 
 constexpr int kStkRB = kStkLead + kStkN + 2;   // rows per channel-chunk plane of a read buffer (212)
 constexpr int kStkPlane = kStkRB * 16;         // bytes per plane (3392)
 constexpr int kStkBuf = kKC * kStkPlane;       // bytes per read buffer (54272)
-constexpr int kStkStageBytes = 8192;   // weight-ring stage = two k-step blocks of 4 KB
-constexpr int kStkStages = 14;         // stages of the weight ring shared by the two slots (>= largest op (13) + prefetch)
+constexpr int kStkStageBytes = 16384;  // weight-ring stage = four k-step blocks of 4 KB
+constexpr int kStkStages = 7;          // stages of the weight ring shared by the two slots (>= the largest op: bottleneck 1 + conv 6)
 constexpr int kStkMaxSeg = 8;          // layers per segment
 constexpr int kStkRegsIssue = 56, kStkRegsEpi = 104;   // setmaxnreg redistributes the launch allocation (640 x 96): 128 x 56 + 512 x 104 = 60416 <= 61440
 constexpr int kStkBmapChunk = 64;       // uint4 per (role, 16-position chunk) of the pool bias map: 32 lanes x 2 (bmap_pack_kernel, dan_bf16.cu)
@@ -90,6 +90,9 @@ struct StackSmem {
   uint64_t acc_full[2], act_ready[2], in_full[2], bott_full[2];
   uint32_t bott_busy, bott_drained;    // the shared bottleneck accumulator: taken by an issuer (CAS 0 -> 1), given back by the last of the 256 epilogue threads that read it out
   uint32_t tmem_base;
+#ifdef DAN_STK_PROF
+  long long t0;
+#endif
   uint32_t issued_ops;                 // ops fully issued by slot 0's issuer (slot 1 runs one op behind, see the issuer)
   float bbias[kStkMaxSeg][kStkBott];
 };
@@ -148,13 +151,21 @@ __device__ __forceinline__ bool named_bar_and(uint32_t id, uint32_t threads, boo
 namespace {
 
 #ifdef DAN_STK_PROF
-#define STK_PROF_DECL long long prof_t0 = clock64(), prof_acc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_begin = prof_t0
-#define STK_PROF(i) do { const long long prof_t1 = clock64(); prof_acc[i] += prof_t1 - prof_t0; prof_t0 = prof_t1; } while (0)
+// besides the per-category sums, CTA 0 logs (category, cycle since CTA start) of every mark of events [kStkTraceSkip, +kStkTraceCap) per role and slot
+constexpr int kStkTraceRead0 = 10, kStkTraceReads = 4, kStkTraceCap = 1024;     // reads [10, 14) of each slot
+#define STK_PROF_DECL long long prof_t0 = clock64(), prof_acc[14] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}; const long long prof_begin = prof_t0; \
+  unsigned long long* prof_tr = nullptr; int prof_n = 0; bool prof_on = false
+#define STK_TRACE_ROLE(cond, r) prof_tr = (blockIdx.x == 0 && (cond)) ? p.prof + (size_t)gridDim.x * 64 + (size_t)(r) * kStkTraceCap : nullptr
+#define STK_PROF(i) do { const long long prof_t1 = clock64(); prof_acc[i] += prof_t1 - prof_t0; prof_t0 = prof_t1; \
+    if (prof_tr && prof_on && prof_n < kStkTraceCap) prof_tr[prof_n++] = ((unsigned long long)(i) << 48) | (unsigned long long)(prof_t1 - sm->t0); } while (0)
+#define STK_TRACE_GATE(rd) prof_on = (rd) >= kStkTraceRead0 && (rd) < kStkTraceRead0 + kStkTraceReads
 #define STK_PROF_FLUSH(cond, base) do { if (cond) { for (int i_ = 0; i_ < 14; ++i_) p.prof[blockIdx.x * 64 + (base) + i_] = prof_acc[i_]; } } while (0)
 #else
 #define STK_PROF_DECL
 #define STK_PROF(i)
 #define STK_PROF_FLUSH(cond, base)
+#define STK_TRACE_ROLE(cond, r)
+#define STK_TRACE_GATE(rd)
 #endif
 
 // descriptor words: lo = (addr >> 4) | (LBO >> 4) << 16, hi = (SBO >> 4) | version 1 << 14  (tcgen05_ptx.cuh make_smem_desc)
@@ -214,6 +225,9 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     for (int i = threadIdx.x; i < 2 * kStkBuf / 16; i += kStkThreads) z[i] = make_uint4(0, 0, 0, 0);
   }
   if (threadIdx.x == 0) {
+#ifdef DAN_STK_PROF
+    sm->t0 = clock64();
+#endif
     for (int i = 0; i < kStkStages; ++i) { mbar_init(&sm->w_full[i], 1); mbar_init(&sm->w_empty[i], 2); }   // both slots release a stage
     sm->issued_ops = 0;
     for (int s = 0; s < 2; ++s) {
@@ -279,7 +293,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     const uint32_t idesc_bott = make_idesc_bf16(128, kStkBott);
     const uint32_t desc_hi = (128u >> 4) | (1u << 14);
     const uint32_t a_lbo_w = (2048u >> 4) << 16, b_lbo_x = ((uint32_t)kStkPlane >> 4) << 16, b_lbo_bott = (((uint32_t)kStkBott * 16u) >> 4) << 16;
-    constexpr int kBottPerStage = kStkStageBytes / (kStkBott * 32);      // k-steps of bottleneck weights per ring stage (8 = all of them)
+    constexpr int kBottPerStage = kKC / 2;                               // the bottleneck's 8 k-steps of weights (8 KB) sit in one ring stage
+    static_assert(kKC / 2 * kStkBott * 32 <= kStkStageBytes, "bottleneck weights must fit one stage");
     const uint32_t ring_lo = smem_u32(rings) >> 4;
     uint64_t* const wfull = &sm->w_full[0];
     uint64_t* const wempty = &sm->w_empty[0];
@@ -293,6 +308,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     // ~190 cycles even when the phase is complete, and there it would sit between the epilogue's hand-over and the op's first MMA.
     bool prewaited = false;
     STK_PROF_DECL;
+    STK_TRACE_ROLE(lane == 0, s);
     auto wait_w = [&]() {
       if (prewaited) { prewaited = false; return; }
       STK_PROF(0);
@@ -374,47 +390,52 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       __syncwarp();
     };
     for (int pr = 0; pr < n_pairs; ++pr) {
+      STK_TRACE_GATE(pr);
       for (int l = 0; l < n_layers; ++l) {
         const StackLayer& L = p.layer[l];
         const int ksteps = L.kc_in / 2, total = L.conv_blocks;
         const uint32_t dil = (uint32_t)L.dil;
         const bool with_bott = highway && l > 0;
         // ---- [bottleneck of layer l-1 +] conv of layer l: D[cout][pos] = sum over taps and input-channel k-steps ----
-        if (with_bott || (ksteps & 3) != 0) prewait1(); else prewait2();
+        if (with_bott || (ksteps & 7) != 0) prewait1(); else prewait2();
         wait_dep(l == 0, (uint32_t)pr);
         if (with_bott) issue_bott();
-        if ((ksteps & 3) == 0) {
-          // two ring stages (4 k-steps) per iteration: both full-barrier probes are in flight together and the four MMAs and
-          // the two stage releases go out from one elected region — a single warp retires a dependent instruction only every
-          // few cycles, so per-stage bookkeeping (not the tensor pipe) bounds the issue rate when it is done stage by stage
+        if ((ksteps & 7) == 0) {
+          // two ring stages (8 k-steps) per iteration: both full-barrier probes are in flight together and the eight MMAs and the two
+          // stage releases go out from one elected region. The issuer shares its scheduler with four epilogue warps whose unrolled ALU
+          // runs keep the issue slot while they are eligible (scripts/probes/issue_probe3.cu: one warp with four independent FFMA chains
+          // doubles the cycles per MMA of this loop, four stretch them tenfold): what counts is the number of issuer instructions — and
+          // dependency stalls, each of which hands the slot away — per MMA, so the bookkeeping is amortised over as many MMAs as a tap has.
           uint32_t acc = 0;
           for (int tap = 0; tap < 3; ++tap) {
             uint32_t bd_lo = (x_lo - dil + (uint32_t)tap * dil) | b_lbo_x;
-            for (int j = 0; j < ksteps; j += 4) {
+            for (int j = 0; j < ksteps; j += 8) {
               const uint32_t wi1 = wi + 1 == kStkStages ? 0u : wi + 1, wp1 = wi1 == 0 ? wp ^ 1u : wp;
               wait_w2(wi1, wp1);
               const uint32_t a0 = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w, a1 = (ring_lo + wi1 * (kStkStageBytes >> 4)) | a_lbo_w;
               if (elect_one()) {
                 umma_bf16(d_main, stk_desc(a0, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, acc);
-                umma_bf16(d_main, stk_desc(a0 + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
-                umma_bf16(d_main, stk_desc(a1, desc_hi), stk_desc(bd_lo + 2 * kStep, desc_hi), idesc_main, 1);
-                umma_bf16(d_main, stk_desc(a1 + 256u, desc_hi), stk_desc(bd_lo + 3 * kStep, desc_hi), idesc_main, 1);
-                umma_commit(&wempty[wi]); umma_commit(&wempty[wi1]);
+#pragma unroll
+                for (uint32_t u = 1; u < 4; ++u) umma_bf16(d_main, stk_desc(a0 + u * 256u, desc_hi), stk_desc(bd_lo + u * kStep, desc_hi), idesc_main, 1);
+                umma_commit(&wempty[wi]);
+#pragma unroll
+                for (uint32_t u = 0; u < 4; ++u) umma_bf16(d_main, stk_desc(a1 + u * 256u, desc_hi), stk_desc(bd_lo + (4 + u) * kStep, desc_hi), idesc_main, 1);
+                umma_commit(&wempty[wi1]);
               }
               __syncwarp();
               acc = 1;
-              bd_lo += 4 * kStep;
+              bd_lo += 8 * kStep;
               adv2(wi1, wp1);
             }
           }
         } else {
           uint32_t bd_lo = x_lo - dil;
           int jj = 0;
-          for (int blk = 0; blk < total; blk += 2) {
+          for (int blk = 0; blk < total; blk += 4) {
             wait_w();
             const uint32_t a_lo = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w;
 #pragma unroll
-            for (int u = 0; u < 2; ++u) {
+            for (int u = 0; u < 4; ++u) {
               if (blk + u < total) {
                 if (elect_one()) umma_bf16(d_main, stk_desc(a_lo + u * 256u, desc_hi), stk_desc(bd_lo | b_lbo_x, desc_hi), idesc_main, (blk + u) > 0);
                 __syncwarp();
@@ -431,20 +452,21 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
         if (L.residual) {
           prewait2();
           wait_dep(false, 0);
-          uint32_t bd_lo = x_lo | b_lbo_x;
-          for (int blk = 0; blk < kKC / 2; blk += 4) {
+          const uint32_t bd_lo = x_lo | b_lbo_x;
+          static_assert(kKC / 2 == 8 && kStkStageBytes == 4 * 4096, "the residual 1x1 (8 k-steps) is two ring stages");
+          {
             const uint32_t wi1 = wi + 1 == kStkStages ? 0u : wi + 1, wp1 = wi1 == 0 ? wp ^ 1u : wp;
             wait_w2(wi1, wp1);
             const uint32_t a0 = (ring_lo + wi * (kStkStageBytes >> 4)) | a_lbo_w, a1 = (ring_lo + wi1 * (kStkStageBytes >> 4)) | a_lbo_w;
             if (elect_one()) {
-              umma_bf16(d_main, stk_desc(a0, desc_hi), stk_desc(bd_lo, desc_hi), idesc_main, 1);
-              umma_bf16(d_main, stk_desc(a0 + 256u, desc_hi), stk_desc(bd_lo + kStep, desc_hi), idesc_main, 1);
-              umma_bf16(d_main, stk_desc(a1, desc_hi), stk_desc(bd_lo + 2 * kStep, desc_hi), idesc_main, 1);
-              umma_bf16(d_main, stk_desc(a1 + 256u, desc_hi), stk_desc(bd_lo + 3 * kStep, desc_hi), idesc_main, 1);
-              umma_commit(&wempty[wi]); umma_commit(&wempty[wi1]);
+#pragma unroll
+              for (uint32_t u = 0; u < 4; ++u) umma_bf16(d_main, stk_desc(a0 + u * 256u, desc_hi), stk_desc(bd_lo + u * kStep, desc_hi), idesc_main, 1);
+              umma_commit(&wempty[wi]);
+#pragma unroll
+              for (uint32_t u = 0; u < 4; ++u) umma_bf16(d_main, stk_desc(a1 + u * 256u, desc_hi), stk_desc(bd_lo + (4 + u) * kStep, desc_hi), idesc_main, 1);
+              umma_commit(&wempty[wi1]);
             }
             __syncwarp();
-            bd_lo += 4 * kStep;
             adv2(wi1, wp1);
           }
           commit_acc();
@@ -512,6 +534,10 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     // bottleneck epilogue of layer lb: tile h, TMEM lane = position 128h + 32q + lane, columns = bottleneck channels; relu(. + bias) -> T
     uint32_t bfc = 0;
     STK_PROF_DECL;
+    STK_TRACE_ROLE(gtid == 0, 2 + s);
+#ifdef DAN_STK_PROF
+    int prof_rd = 0;
+#endif
     auto bott_epilogue = [&](int lb, int read_global, bool valid) {
       STK_PROF(0);
       mbar_wait(&sm->bott_full[s], bfc & 1);
@@ -522,7 +548,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       tmem_ld32(tbott, r);
       tmem_ld_wait();
       tc_fence_before();
-      if (atomicAdd(&sm->bott_drained, 1u) == kStkEpiThreads - 1) {      // the accumulator has been read out by all: the next bottleneck MMAs (either slot) may overwrite it
+      __syncwarp();
+      if (lane == 0 && atomicAdd(&sm->bott_drained, 1u) == kStkEpiThreads / 32 - 1) {   // read out by all 8 warps: the next bottleneck MMAs (either slot) may overwrite it
         sm->bott_drained = 0;
         __threadfence_block();
         atomicExch(&sm->bott_busy, 0u);
@@ -553,6 +580,9 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
     uint32_t opc = 0;
     while (!it.done()) {
+#ifdef DAN_STK_PROF
+      STK_TRACE_GATE(prof_rd); ++prof_rd;
+#endif
       const bool valid = it.valid(p.R, s);
       const int cand = it.cand;
       const int read_global = cand * p.R + it.read_in_cand(s);

@@ -5,7 +5,7 @@
 #include "../../dl4vc_b200/csrc/tcgen05_ptx.cuh"
 using namespace ptx;
 
-struct Cfg { int M, N, a_lbo, b_lbo, b_off, commit_every, iters, mode; };
+struct Cfg { int M, N, a_lbo, b_lbo, b_off, commit_every, iters, mode, acc_stride = 256, a_tiles = 8; };
 
 __global__ void __launch_bounds__(128, 1) probe(Cfg c, long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -46,12 +46,12 @@ __global__ void __launch_bounds__(128, 1) probe(Cfg c, long long* out) {
       if (c.mode == 1) {
         if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) umma_bf16(tm + (k & 1) * 256, ad0 + (uint64_t)(k * 256), bd0 + (uint64_t)((k & 3) * 2 * (c.b_lbo >> 4)), idesc, 1);
+          for (int k = 0; k < 8; ++k) umma_bf16(tm + (k & 1) * c.acc_stride, ad0 + (uint64_t)((k % c.a_tiles) * 256), bd0 + (uint64_t)((k & 3) * 2 * (c.b_lbo >> 4)), idesc, 1);
         }
         __syncwarp();
       } else {
 #pragma unroll
-        for (int k = 0; k < 8; ++k) { if (elect_one()) umma_bf16(tm + (k & 1) * 256, ad0 + (uint64_t)(k * 256), bd0 + (uint64_t)((k & 3) * 2 * (c.b_lbo >> 4)), idesc, 1); __syncwarp(); }
+        for (int k = 0; k < 8; ++k) { if (elect_one()) umma_bf16(tm + (k & 1) * c.acc_stride, ad0 + (uint64_t)((k % c.a_tiles) * 256), bd0 + (uint64_t)((k & 3) * 2 * (c.b_lbo >> 4)), idesc, 1); __syncwarp(); }
       }
       if (c.commit_every) { if (elect_one()) umma_commit(&bar); __syncwarp(); mbar_wait(&bar, phase); phase ^= 1; }
     }
@@ -79,16 +79,20 @@ int main() {
     {128, 64, 2048, 1024, 0, 0, 2000, 1},     // N=64
     {128, 32, 3392, 512, 0, 0, 2000, 1},      // bottleneck orientation: A=activations, N=32
     {128, 208, 2048, 3392, 32, 8, 2000, 1},   // commit + wait every 8 MMAs (serialised)
+    {128, 208, 2048, 3392, 32, 0, 2000, 1, 0, 8},   // ONE accumulator
+    {128, 208, 2048, 3392, 32, 0, 2000, 2, 0, 8},   // ONE accumulator, elect per MMA
+    {128, 208, 2048, 3392, 32, 0, 2000, 1, 0, 2},   // ONE accumulator, 2 A tiles
+    {128, 208, 2048, 3392, 32, 0, 2000, 1, 256, 2}, // two accumulators, 2 A tiles
   };
-  for (int grid : {148}) {
+  for (int grid : {1, 148}) {
     for (auto& c : cfgs) {
       probe<<<grid, 128, 200 * 1024>>>(c, d);
       cudaError_t e = cudaDeviceSynchronize();
       if (e != cudaSuccess) { printf("error %s\n", cudaGetErrorString(e)); return 1; }
       long long h[148]; cudaMemcpy(h, d, grid * 8, cudaMemcpyDeviceToHost);
       double m = 0; for (int i = 0; i < grid; ++i) m += (double)h[i] / grid;
-      printf("mode %d grid %3d  M %3d N %3d a_lbo %4d b_lbo %4d b_off %2d commit_every %d : %.1f cycles/MMA (ideal %.0f)\n", c.mode, grid, c.M, c.N, c.a_lbo, c.b_lbo,
-             c.b_off, c.commit_every, m / c.iters, 128.0 * c.N / 256.0);
+      printf("mode %d grid %3d  M %3d N %3d a_lbo %4d b_lbo %4d b_off %2d commit_every %d acc_stride %d a_tiles %d : %.1f cycles/MMA (ideal %.0f)\n", c.mode, grid, c.M, c.N, c.a_lbo, c.b_lbo,
+             c.b_off, c.commit_every, c.acc_stride, c.a_tiles, m / c.iters, 128.0 * c.N / 256.0);
     }
   }
   return 0;
