@@ -228,7 +228,7 @@ def fp32_block(model, sample, dev, cfg, clocks, batch=592, steps=3):
                          "peak_source": "nominal: 148 SMs x 128 FMA lanes x 2 x sm_max_mhz"}}
 
 
-def train_step_block(cfg, sd, dev, dist, world, rank, timed, batch=32, steps=3):
+def train_step_block(cfg, sd, dev, dist, world, rank, timed, batch=32, steps=3, e2e=False):
     """BASELINE configs[4]: one data-parallel training step per rank = training-mode forward (batch-statistics BatchNorm, dropout 0.1, read
     removal) -> device loss block (dan_losses) -> native backward -> bucketed gradient all-reduce over NCCL -> grad clip 1.0 -> Adam, with the
     close-example flags scattered into the device-resident table (easy-example down-sampling input). fp32 kernels; `value` counts the
@@ -267,11 +267,30 @@ def train_step_block(cfg, sd, dev, dist, world, rank, timed, batch=32, steps=3):
     for _ in range(2):
         step()
     ms = timed(step, steps)
+    launches = getattr(model, "last_train_launch_count", 0) + 2          # + dan_losses_kernel, close_table_update_kernel
+    extra = {}
+    if e2e:
+        # the step a trainer runs per batch: pinned host uint8 tensors + labels -> device, the step, the loss block back to the host
+        host = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in b.arrays()]
+        lab_host = [t.cpu().pin_memory() for t in (tb, vt, af, cov, vb, vr)]
+        loss_host = torch.empty(8, dtype=torch.float32).pin_memory()
+
+        def step_e2e():
+            nonlocal d, tb, vt, af, cov, vb, vr
+            d = [t.to(dev, non_blocking=True) for t in host]
+            tb, vt, af, cov, vb, vr = [t.to(dev, non_blocking=True) for t in lab_host]
+            step()
+            loss_host.copy_(state["loss"].reshape(-1)[:8], non_blocking=True)
+
+        step_e2e()
+        ms_e2e = timed(step_e2e, steps)
+        extra = {"e2e_ms": ms_e2e, "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in host + lab_host), "d2h_bytes_per_step": 32,
+                 "launches_per_step": launches}
     grad_bytes = sum(p.numel() for p in model.parameters() if p.requires_grad) * 4
     loss = [round(float(x), 4) for x in state["loss"].cpu()]
     del model, opt
     torch.cuda.empty_cache()
-    return {"value": batch * world * steps / (ms * 1e-3), "unit": "candidates/s (training step)", "batch_per_gpu": batch, "steps": steps, "ms_per_step": ms / steps,
+    return {**extra, "value": batch * world * steps / (ms * 1e-3), "unit": "candidates/s (training step)", "batch_per_gpu": batch, "steps": steps, "ms_per_step": ms / steps,
             "dtype": "f32", "collective": None if world == 1 else f"NCCL all-reduce (sum / {world}) of {grad_bytes / 1e6:.0f} MB fp32 gradients per step in 2 buckets "
                                                                     "(FC trunk + heads first, on a side stream), BatchNorm statistics per GPU",
             "step": "train forward + dan_losses + dan_backward + gradient all-reduce + clip_grad_norm 1.0 + Adam + close-table scatter",
@@ -351,6 +370,29 @@ def run_b200(args):
             ms = float(t.item())
         barrier()
         return ms
+
+    if args.mode == "train":
+        # BASELINE configs[4] as a line of its own: python bench.py --mode train [--gpus N under torchrun]
+        sampler = ClockSampler(local)
+        sampler.start()
+        tb = train_step_block(cfg, sd, dev, dist, world, rank, timed, batch=args.train_batch, steps=args.steps, e2e=True)
+        clocks = sampler.stop()
+        if rank == 0:
+            n = args.train_batch * world * args.steps
+            print(json.dumps({
+                "metric": "candidate variants/sec (DAN training step)", "value": tb["value"], "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
+                "warmup": 2, "ms_per_step": tb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "mode": "train",
+                "config": {"workload": "PROD DAN training step (train_variant_caller.sh flag set): " + tb["step"], "candidates_per_step_per_gpu": args.train_batch,
+                           "model": "PROD", "parallelism": f"data-parallel x{world}", "collective": tb["collective"],
+                           "l2_policy": "activation tape of a step (GBs) exceeds the 126 MB L2, no flush"},
+                "e2e": {"value": n / (tb["e2e_ms"] * 1e-3), "unit": "candidates/s", "h2d_bytes_per_step": tb["h2d_bytes_per_step"],
+                        "d2h_bytes_per_step": tb["d2h_bytes_per_step"], "ms_per_step": tb["e2e_ms"] / args.steps},
+                "gpu_launches": tb["launches_per_step"] * args.steps, "clocks": clocks,
+                "last_losses[bin,vt,af,cov,vb,vr,total,n_close]": tb["last_losses[bin,vt,af,cov,vb,vr,total,n_close]"]}), flush=True)
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
 
     def step_resident():
         return model.forward_heads(d_r, d_ref, d_q, d_s, d_rm, d_vm)
@@ -471,6 +513,8 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--batch", type=int, default=4144, help="candidates per step per GPU (28 passes of 148 candidates)")
     ap.add_argument("--pass-candidates", type=int, default=0)
+    ap.add_argument("--mode", default="forward", choices=["forward", "train"], help="train: the data-parallel training step (BASELINE configs[4]) as its own line")
+    ap.add_argument("--train-batch", type=int, default=32, help="candidates per training step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32 1e-4-parity path block (BASELINE configs[1])")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step block (BASELINE configs[4])")

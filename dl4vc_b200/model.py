@@ -536,6 +536,7 @@ class Basic2DNet(nn.Module):
             stream = torch.cuda.current_stream(dev).cuda_stream
             _lib.check(lib.dan_train_forward(st.handle, _lib.C.byref(w), p(u8[0]), p(u8[1]), p(u8[2]), p(u8[3]), p(u8[4]), p(u8[5]), p(removed), B,
                                              float(dropout_p), int(seed), out.data_ptr(), tape.data_ptr(), tape.numel(), stream), "dan_train_forward")
+            self.last_train_launch_count = lib.dan_last_launch_count()
             if self.dan_config.use_batchnorm:
                 for bn in self.bn1D_layers:              # like nn.BatchNorm2d in training mode; also tells the packed-weight cache that buffers moved
                     bn.num_batches_tracked += 1
@@ -566,6 +567,7 @@ class Basic2DNet(nn.Module):
             _lib.check(lib.dan_backward(st.handle, _lib.C.byref(w), p(u8[0]), p(u8[1]), p(u8[2]), p(u8[3]), p(u8[4]), p(u8[5]), p(removed), B,
                                         float(dropout_p), int(seed), dheads.data_ptr(), heads.data_ptr(), _lib.C.byref(gw), tape.data_ptr(), tape.numel(),
                                         stream), "dan_backward")
+            self.last_train_launch_count = getattr(self, "last_train_launch_count", 0) + lib.dan_last_launch_count()
             out, row = [], 0
             for name, t in params:
                 if name.startswith("head_w."):
