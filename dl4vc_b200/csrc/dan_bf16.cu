@@ -355,7 +355,9 @@ __global__ void pack_linear_bf16_kernel(const float* __restrict__ w, uint4* __re
   }
 }
 
-// per-layer epilogue constants [4][128]: conv bias | BN scale | BN shift | residual bias (built on the device from the fp32 store)
+// per-layer epilogue constants [6][128]: conv bias | BN scale | BN shift | residual bias | -bias | scale * bias + shift (built on the
+// device from the fp32 store; the last two are what the stack kernel's FMNMX + FFMA epilogue uses, dan_stack_epi.cuh)
+constexpr int kChanRows = 6;
 __global__ void chan_table_kernel(const float* __restrict__ bias, const float* __restrict__ scale, const float* __restrict__ shift,
                                   const float* __restrict__ rbias, float* __restrict__ out) {
   const int c = threadIdx.x;
@@ -363,6 +365,8 @@ __global__ void chan_table_kernel(const float* __restrict__ bias, const float* _
   out[kC + c] = scale ? scale[c] : 1.f;
   out[2 * kC + c] = shift ? shift[c] : 0.f;
   out[3 * kC + c] = rbias ? rbias[c] : 0.f;
+  out[4 * kC + c] = -bias[c];
+  out[5 * kC + c] = fmaf(scale ? scale[c] : 1.f, bias[c], shift ? shift[c] : 0.f);
 }
 
 struct Bf16Weights {
@@ -373,7 +377,7 @@ struct Bf16Weights {
   const float** comp_bias_ptrs;       // device array of L pointers
   uint8_t* wstream[DAN_MAX_LAYERS];   // conv | residual | bottleneck operand images of a layer, contiguous (dan_stack.cuh); kWeightReplicas copies
   size_t wstream_bytes[DAN_MAX_LAYERS];   // bytes of one copy (256-byte multiple)
-  float* chan_dev;                    // [L][4][128] conv bias, BN scale, BN shift, residual bias (device)
+  float* chan_dev;                    // [L][6][128] epilogue constants (chan_table_kernel)
   uint4* enc_tab;                     // [P][10][3] pieces: bf16(E[tok] + pe[p]) (enc_table_kernel)
   int num_sms;
 };
@@ -489,7 +493,7 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
     return DAN_OK;
   };
   int rc;
-  if (!bw->chan_dev) DAN_CUDA_TRY(cudaMalloc(&bw->chan_dev, sizeof(float) * DAN_MAX_LAYERS * 4 * kC));
+  if (!bw->chan_dev) DAN_CUDA_TRY(cudaMalloc(&bw->chan_dev, sizeof(float) * DAN_MAX_LAYERS * kChanRows * kC));
   for (int l = 0; l < L; ++l) {
     const int cin = l == 0 ? m->Cin : kC, kc_in = (l == 0 ? m->CinPad : kC) / 8;
     if (!bw->wstream[l]) {
@@ -517,7 +521,7 @@ int dan_bf16_pack(dan_model* m, const dan_weights* w, cudaStream_t st) {
     }
     // epilogue constants (the fp32 packer already folded BatchNorm on this stream)
     chan_table_kernel<<<1, kC, 0, st>>>(m->convB[l], m->cfg.use_batchnorm ? m->bnScale[l] : nullptr, m->cfg.use_batchnorm ? m->bnShift[l] : nullptr,
-                                        m->cfg.is_residual[l] ? m->resB[l] : nullptr, bw->chan_dev + (size_t)l * 4 * kC);
+                                        m->cfg.is_residual[l] ? m->resB[l] : nullptr, bw->chan_dev + (size_t)l * kChanRows * kC);
   }
   int K = m->fcIn, Kpad = m->fcInPad;
   for (int i = 0; i < m->cfg.num_fc; ++i) {
@@ -614,7 +618,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
     sp.cands = ns; sp.R = R; sp.P = P; sp.pitch = g.pitch; sp.highway = m->cfg.highway; sp.num_layers = l_end - l;
     for (int k = l; k < l_end; ++k) {
       StackLayer& SL = sp.layer[k - l];
-      SL.wstream = bw->wstream[k]; SL.wreplica_stride = bw->wstream_bytes[k]; SL.chan = bw->chan_dev + (size_t)k * 4 * kC; SL.bbias = m->bottB[k];
+      SL.wstream = bw->wstream[k]; SL.wreplica_stride = bw->wstream_bytes[k]; SL.chan = bw->chan_dev + (size_t)k * kChanRows * kC; SL.bbias = m->bottB[k];
       SL.tout = T + (long)k * pl.t_layer_pieces;
       SL.kc_in = (k == 0 ? m->CinPad : kC) / 8; SL.conv_blocks = 3 * SL.kc_in / 2;
       SL.dil = m->cfg.dilation[k]; SL.residual = m->cfg.is_residual[k];
@@ -746,7 +750,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           lp.wconv = bw->wconv[l]; lp.wres = bw->wres[l]; lp.wbott = bw->wbott[l];
           lp.rows_total = rows; lp.num_tiles = num_tiles; lp.pitch = g.pitch; lp.P = P; lp.gap = g.gap; lp.dil = m->cfg.dilation[l];
           lp.kc_in = (l == 0 ? m->CinPad : kC) / 8; lp.residual = m->cfg.is_residual[l]; lp.highway = m->cfg.highway; lp.bott = bott;
-          lp.chan = bw->chan_dev + (size_t)l * 4 * kC; lp.bbias = m->bottB[l];
+          lp.chan = bw->chan_dev + (size_t)l * kChanRows * kC; lp.bbias = m->bottB[l];
           const size_t smem = layer_smem_bytes(lp.kc_in, lp.residual, lp.highway, bott, g.gap);
           int grid = (num_tiles + kSlots - 1) / kSlots;
           if (grid > bw->num_sms) grid = bw->num_sms;

@@ -61,7 +61,7 @@ enum { kStkInPlanes = 0, kStkInEncode = 1 };
 struct StackLayer {
   const uint8_t* wstream;   // conv k-step blocks (tap-major) | residual blocks | bottleneck blocks, contiguous
   size_t wreplica_stride;   // byte distance between the kWeightReplicas copies of wstream
-  const float* chan;        // [4][128]: conv bias, BN scale, BN shift, residual bias
+  const float* chan;        // [6][128] epilogue constants (dan_bf16.cu chan_table_kernel)
   const float* bbias;       // [bott]
   uint4* tout;              // T[read][c/8][p][c%8] (bf16) of this layer: row-major A operand (K = (c/8, p, c%8)) of the compression GEMM
   int conv_blocks;          // 3 * kc_in / 2
@@ -595,9 +595,10 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int c = 32 * q + 8 * j + (lane >> 2);
-          const float b = with_bmap ? 0.f : __ldg(L.chan + c);
+          // y = scale * max(z, -b) + (scale * b + shift); with the pool bias map the conv bias is inside the map: max(z, -0) and shift alone
           k.scale[j] = __ldg(L.chan + kC + c); k.rbias[j] = __ldg(L.chan + 3 * kC + c);
-          k.c[j] = fmaf(k.scale[j], b, __ldg(L.chan + 2 * kC + c)); k.nb[j] = -b;
+          k.nb[j] = with_bmap ? -0.f : __ldg(L.chan + 4 * kC + c);
+          k.c[j] = __ldg(L.chan + (with_bmap ? 2 : 5) * kC + c);
         }
         // pool bias map of this read's candidate, this thread's fragments: the first four chunks are requested before the
         // accumulator is awaited (their L2 latency hides under the conv MMAs), the rest as the chunks are consumed
