@@ -11,6 +11,7 @@ import os
 
 DAN_MAX_LAYERS = 12
 DAN_MAX_FC = 4
+VOCAB = 10              # DAN_VOCAB: rows of the embedding table (model.py:206)
 NUM_HEAD_OUTPUTS = 27
 PRECISION_FP32 = 0
 PRECISION_BF16 = 1

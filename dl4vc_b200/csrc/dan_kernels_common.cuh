@@ -84,11 +84,11 @@ __device__ inline float encode_channel(const EncodeParams& p, const EncodeSmem& 
   const int D = p.D, R = p.g.R;
   if (s.removed && s.removed[r]) {      // the row of an empty read: pad embedding + reference, every other channel zero (model.py:519-568)
     if (c < D) return s.emb[c] + __ldg(p.pe + pp * D + c);
-    if (c < 2 * D) return s.emb[s.ref[pp] * D + (c - D)] + __ldg(p.pe + pp * D + (c - D));
+    if (c < 2 * D) return s.emb[min((int)s.ref[pp], DAN_VOCAB - 1) * D + (c - D)] + __ldg(p.pe + pp * D + (c - D));
     return 0.f;
   }
-  if (c < D) return s.emb[s.reads[pp * R + r] * D + c] + __ldg(p.pe + pp * D + c);
-  if (c < 2 * D) return s.emb[s.ref[pp] * D + (c - D)] + __ldg(p.pe + pp * D + (c - D));
+  if (c < D) return s.emb[min((int)s.reads[pp * R + r], DAN_VOCAB - 1) * D + c] + __ldg(p.pe + pp * D + c);
+  if (c < 2 * D) return s.emb[min((int)s.ref[pp], DAN_VOCAB - 1) * D + (c - D)] + __ldg(p.pe + pp * D + (c - D));
   c -= 2 * D;
   if (p.use_q) { if (c == 0) return (float)s.q[pp * R + r] * 0.01f; --c; }       // Q_SCORE_SCALE_FACTOR, model.py:24
   if (p.use_s) { if (c == 0) return (float)s.st[pp * R + r] * 0.5f; --c; }       // STRAND_ENCODE_FACTOR, model.py:16

@@ -81,6 +81,7 @@ class _DanTrainFunction(torch.autograd.Function):
 
 
 class Basic2DNet(nn.Module):
+    check_tokens = False       # range-check device-resident int64 token inputs before narrowing (synchronises); CPU inputs are always checked
     def __init__(self, target_size, layer_sizes=[1024, 256], pre_conv_dropout=0.1, hidden_dropout=0.1,
                  embed_dim=20, pos_embeddings=True, init_conv_channels=CONV_CHANNELS, final_conv_channels=CONV_CHANNELS,
                  ref_concat_at_reads=True, split_ref_reads_groups=False,
@@ -364,10 +365,15 @@ class Basic2DNet(nn.Module):
         return ws
 
     @staticmethod
-    def _u8(t, dev):
+    def _u8(t, dev, vocab=0):
+        """vocab > 0: `t` holds embedding tokens. nn.Embedding raises on a token outside [0, vocab) (model.py:450-459); the kernels
+        clamp instead of faulting, so wider-than-uint8 inputs are range-checked before they are narrowed — always for CPU tensors, for
+        device tensors only with Basic2DNet.check_tokens (the check synchronises)."""
         if t is None:
             return None
         if t.dtype != torch.uint8:
+            if vocab and t.numel() and (t.device.type == "cpu" or Basic2DNet.check_tokens) and (int(t.min()) < 0 or int(t.max()) >= vocab):
+                raise IndexError(f"token outside [0, {vocab}) in an embedding input (nn.Embedding would raise 'index out of range in self')")
             t = t.to(torch.uint8)           # narrow on the source device first (the trainer hands int64, trainer.py:520-528)
         return t.to(dev, non_blocking=True).contiguous()
 
@@ -385,7 +391,7 @@ class Basic2DNet(nn.Module):
             P, R = self.single_read_len, self.num_single_reads
             if tuple(reads.shape[1:]) != (P, R):
                 raise RuntimeError(f"reads must be (batch, {P}, {R}) [batch, position, read] (dataset.py:672-680), got {tuple(reads.shape)}")
-            r8, f8 = self._u8(reads, dev), self._u8(ref, dev)
+            r8, f8 = self._u8(reads, dev, _lib.VOCAB), self._u8(ref, dev, _lib.VOCAB)
             q8 = self._u8(q_scores, dev) if self.use_q_scores else None
             s8 = self._u8(strands, dev) if self.use_strands else None
             rm8 = self._u8(ref_masks, dev) if self.use_reads_ref_var_mask else None
@@ -410,12 +416,14 @@ class Basic2DNet(nn.Module):
         dev = self._device()
         lib = _lib.load_library()
 
-        def host_u8(t, used=True):
+        def host_u8(t, used=True, vocab=0):
             if t is None or not used:
                 return None
             if t.device.type != "cpu":
                 raise RuntimeError("forward_heads_host takes CPU tensors; use forward_heads for device tensors")
             if t.dtype != torch.uint8:
+                if vocab and t.numel() and (int(t.min()) < 0 or int(t.max()) >= vocab):
+                    raise IndexError(f"token outside [0, {vocab}) in an embedding input (nn.Embedding would raise 'index out of range in self')")
                 t = t.to(torch.uint8)
             return t.contiguous()
 
@@ -426,7 +434,7 @@ class Basic2DNet(nn.Module):
             P, R = self.single_read_len, self.num_single_reads
             if tuple(reads.shape[1:]) != (P, R):
                 raise RuntimeError(f"reads must be (batch, {P}, {R}) [batch, position, read] (dataset.py:672-680), got {tuple(reads.shape)}")
-            r8, f8 = host_u8(reads), host_u8(ref)
+            r8, f8 = host_u8(reads, vocab=_lib.VOCAB), host_u8(ref, vocab=_lib.VOCAB)
             q8, s8 = host_u8(q_scores, self.use_q_scores), host_u8(strands, self.use_strands)
             rm8, vm8 = host_u8(ref_masks, self.use_reads_ref_var_mask), host_u8(var_masks, self.use_reads_ref_var_mask)
             if out is None:
@@ -489,8 +497,8 @@ class Basic2DNet(nn.Module):
         P, R = self.single_read_len, self.num_single_reads
         if tuple(reads.shape[1:]) != (P, R):
             raise RuntimeError(f"reads must be (batch, {P}, {R}) [batch, position, read] (dataset.py:672-680), got {tuple(reads.shape)}")
-        return (self._u8(reads, dev), self._u8(q_scores, dev) if self.use_q_scores else None, self._u8(strands, dev) if self.use_strands else None,
-                self._u8(ref, dev), self._u8(ref_masks, dev) if self.use_reads_ref_var_mask else None,
+        return (self._u8(reads, dev, _lib.VOCAB), self._u8(q_scores, dev) if self.use_q_scores else None, self._u8(strands, dev) if self.use_strands else None,
+                self._u8(ref, dev, _lib.VOCAB), self._u8(ref_masks, dev) if self.use_reads_ref_var_mask else None,
                 self._u8(var_masks, dev) if self.use_reads_ref_var_mask else None)
 
     def _choose_removed(self, u8, rm_non_var_reads, rm_var_reads):
@@ -611,7 +619,7 @@ class Basic2DNet(nn.Module):
             st = self._state(dev)
             B = int(reads.shape[0])
             out = torch.empty((B, self.dan_config.in_channels, self.num_single_reads, self.single_read_len), dtype=torch.float32, device=dev)
-            r8, f8 = self._u8(reads, dev), self._u8(ref, dev)
+            r8, f8 = self._u8(reads, dev, _lib.VOCAB), self._u8(ref, dev, _lib.VOCAB)
             q8 = self._u8(q_scores, dev) if self.use_q_scores else None
             s8 = self._u8(strands, dev) if self.use_strands else None
             rm8 = self._u8(ref_masks, dev) if self.use_reads_ref_var_mask else None

@@ -104,3 +104,18 @@ def test_config_struct_matches_header_layout():
     assert list(c.is_residual)[:7] == [0, 0, 0, 0, 1, 1, 1]
     assert list(c.pool_after)[:7] == [0, 1, 0, 0, 0, 0, 0]
     assert list(c.fc_sizes)[:2] == [1024, 256]
+
+
+def test_out_of_range_tokens_raise_like_nn_embedding():
+    """nn.Embedding raises IndexError on a token outside the table (model.py:450-459); int64 inputs are range-checked before they are
+    narrowed to the kernels' uint8 (a silent wrap would index another row)."""
+    import torch
+    from dl4vc_b200 import _lib
+    from dl4vc_b200.model import Basic2DNet
+
+    ok = torch.tensor([[0, 9, 3]], dtype=torch.int64)
+    assert Basic2DNet._u8(ok, "cpu", _lib.VOCAB).dtype == torch.uint8
+    for bad in (torch.tensor([[0, 10]], dtype=torch.int64), torch.tensor([[-1, 2]], dtype=torch.int64), torch.tensor([[266]], dtype=torch.int64)):
+        with pytest.raises(IndexError):
+            Basic2DNet._u8(bad, "cpu", _lib.VOCAB)
+    assert Basic2DNet._u8(torch.tensor([[200]], dtype=torch.int64), "cpu").item() == 200      # q-scores / strands / masks: plain bytes
