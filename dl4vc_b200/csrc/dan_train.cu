@@ -21,24 +21,37 @@ constexpr float kBnMomentum = 0.1f, kBnEps = 1e-5f;      // nn.BatchNorm2d defau
 
 // ------------------------------------------------------------------------------------------------ column reductions
 // part[chunk][which][c]: MODE 0: sum x | sum x^2 ; MODE 1: sum dy | sum dy * xhat, xhat = (u - mean) * rstd ; MODE 2: sum x
+constexpr int kRedLanes = 4;             // row lanes per column: threads (c, lane) walk rows lane, lane + 4, ... of the partial's range
 template <int MODE>
-__global__ void __launch_bounds__(128) col_reduce_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ U, int ldu,
-                                                         const double* __restrict__ mean, const double* __restrict__ rstd, long rows, int C,
-                                                         RowGeom g, int masked, double* __restrict__ part) {
-  const int c = blockIdx.y * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(128 * kRedLanes) col_reduce_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ U, int ldu,
+                                                                     const double* __restrict__ mean, const double* __restrict__ rstd, long rows, int C,
+                                                                     RowGeom g, int masked, double* __restrict__ part) {
+  __shared__ double sh[2][kRedLanes][128];
+  const int tx = threadIdx.x & 127, ry = threadIdx.x >> 7;
+  const int c = blockIdx.y * 128 + tx;
   const long r0 = (long)blockIdx.x * kRedRows, r1 = r0 + kRedRows < rows ? r0 + kRedRows : rows;
   double s0 = 0.0, s1 = 0.0;
   if (c < C) {
     const double mu = MODE == 1 ? mean[c] : 0.0, rs = MODE == 1 ? rstd[c] : 0.0;
-    for (long r = r0; r < r1; ++r) {
-      if (masked && (int)(r % g.pitch) >= g.P) continue;
-      const float x = X[r * ldx + c];
+    int rp = masked ? (int)((r0 + ry) % g.pitch) : 0;                  // position of the row inside its read (rows >= P are gap rows)
+#pragma unroll 4
+    for (long r = r0 + ry; r < r1; r += kRedLanes) {
+      const bool ok = !masked || rp < g.P;
+      const float x = ok ? X[r * ldx + c] : 0.f;
       if (MODE == 0) { s0 += x; s1 += (double)x * x; }
-      else if (MODE == 1) { s0 += x; s1 += (double)x * (((double)U[r * ldu + c] - mu) * rs); }
+      else if (MODE == 1) { const float u = ok ? U[r * ldu + c] : 0.f; s0 += x; s1 += (double)x * (((double)u - mu) * rs); }
       else s0 += x;
+      if (masked) { rp += kRedLanes; if (rp >= g.pitch) rp -= g.pitch; }
     }
-    part[((long)blockIdx.x * 2 + 0) * C + c] = s0;
-    part[((long)blockIdx.x * 2 + 1) * C + c] = s1;
+  }
+  sh[0][ry][tx] = s0; sh[1][ry][tx] = s1;
+  __syncthreads();
+  if (ry == 0 && c < C) {              // lanes added in a fixed order
+    double a0 = sh[0][0][tx], a1 = sh[1][0][tx];
+#pragma unroll
+    for (int k = 1; k < kRedLanes; ++k) { a0 += sh[0][k][tx]; a1 += sh[1][k][tx]; }
+    part[((long)blockIdx.x * 2 + 0) * C + c] = a0;
+    part[((long)blockIdx.x * 2 + 1) * C + c] = a1;
   }
 }
 __global__ void bn_stats_finish_kernel(const double* __restrict__ part, int chunks, int C, double N, double* __restrict__ mean, double* __restrict__ rstd,
@@ -333,6 +346,13 @@ inline int grid1d(long total, int block = 256) {
   return (int)(gsz < 1 ? 1 : (gsz > 148 * 16 ? 148 * 16 : gsz));
 }
 
+// row ranges of a weight-gradient product (sgemm_tn_kernel): two CTAs per SM on a 148-SM part once the problem is large enough
+inline int tn_splits(long rows) {
+  int splits = (int)(rows / 2048);
+  return splits < 1 ? 1 : (splits > 296 ? 296 : splits);
+}
+constexpr int kLinearMaxSplits = 40;
+
 struct TrainPlan {
   long rows, rowsAlloc, readsPad, hw_layer_stride;
   int BPad, chunks;
@@ -379,8 +399,10 @@ TrainPlan make_train_plan(const dan_model* m, int B) {
   pl.dhw = take((size_t)L * pl.hw_layer_stride * 4);
   pl.dfc[0] = take((size_t)pl.BPad * m->fcInPad * 4); pl.dfc[1] = take((size_t)pl.BPad * m->fcInPad * 4);
   pl.dz_heads = take((size_t)pl.BPad * DAN_HEAD_PAD * 4);
-  int splits = (int)(pl.rows / 8192); if (splits < 1) splits = 1; if (splits > 296) splits = 296;
+  int splits = tn_splits(pl.rows);
   pl.tn_part_floats = (size_t)splits * 128 * 128 + (size_t)64 * bott * g.pitch * bott;      // conv-shaped problems | compression (I = bott, J = P*bott)
+  const size_t fc_part = (size_t)kLinearMaxSplits * pl.BPad * 1024;                          // split-K partials of the small-M FC products (tr_linear)
+  if (pl.tn_part_floats < fc_part) pl.tn_part_floats = fc_part;
   pl.tnpart = take(pl.tn_part_floats * 4);
   size_t wt = (size_t)3 * C * (C > m->CinPad ? C : m->CinPad);
   if ((size_t)bott * m->P * bott > wt) wt = (size_t)bott * m->P * bott;
@@ -394,19 +416,35 @@ TrainPlan make_train_plan(const dan_model* m, int B) {
 
 int tr_gemm(const GemmParams& p, cudaStream_t st) { return launch_gemm(p, st); }
 
-// y = [relu](x W + b) for a row-major activation matrix x [M][lda] and a K-major weight W[k][n]
-int tr_linear(const float* A, int lda, int M, int K, const float* W, int N, int ldw, const float* bias, int relu, const float* resid, int ldr, float* out, int ldo, cudaStream_t st) {
+// y = [relu](x W + b) for a row-major activation matrix x [M][lda] and a K-major weight W[k][n]. A batch-sized M with a long K (FC1:
+// 32 x 73 856 -> 1024) would run on N / 128 CTAs: such products go split-K over fixed K ranges (partials in `part`, added in order by
+// splitk_finish_kernel), enough ranges for two CTAs per SM.
+int tr_linear(const float* A, int lda, int M, int K, const float* W, int N, int ldw, const float* bias, int relu, const float* resid, int ldr, float* out, int ldo,
+              float* part, size_t part_floats, cudaStream_t st) {
   GemmParams q{};
   q.A = A; q.lda = lda; q.a_rows = M; q.M = M; q.ntaps = 1; q.tap_off[0] = 0; q.Kc = K;
   q.W = W; q.N = N; q.ldw = ldw; q.bias = bias; q.relu = relu; q.resid = resid; q.ldr = ldr; q.out = out; q.ldo = ldo; q.splits = 1;
-  return launch_gemm(q, st);
+  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+  int splits = 1;
+  if (part && !resid && tiles < 74 && K >= 4096) {
+    splits = (296 + tiles - 1) / tiles;
+    if (splits > kLinearMaxSplits) splits = kLinearMaxSplits;
+    if (splits > K / 64) splits = K / 64;
+    while (splits > 1 && (size_t)splits * M * N > part_floats) --splits;
+  }
+  if (splits <= 1) return launch_gemm(q, st);
+  q.out = part; q.ldo = N; q.splits = splits; q.split_stride = (long)M * N; q.bias = nullptr; q.relu = 0;
+  int rc = launch_gemm(q, st);
+  if (rc) return rc;
+  splitk_finish_kernel<<<grid_for((long)M * N), 256, 0, st>>>(part, splits, q.split_stride, M, N, N, bias, relu, 0, out, ldo);
+  dan_count_launch();
+  DAN_CUDA_TRY(cudaGetLastError());
+  return DAN_OK;
 }
 
 // out[i * rs + j * cs] = sum_m A[m][i] * B[m + b_off][j]
 int tr_wgrad(const float* A, int lda, const float* B, int ldb, long rows, int b_off, int I, int J, int Jkeep, float* out, long rs, long cs, float* part, size_t part_floats, cudaStream_t st) {
-  int splits = (int)(rows / 8192);
-  if (splits < 1) splits = 1;
-  if (splits > 296) splits = 296;
+  int splits = tn_splits(rows);
   while (splits > 1 && (size_t)splits * I * J > part_floats) --splits;
   TnParams p{A, lda, B, ldb, rows, b_off, I, J, part, splits, out, rs, cs, Jkeep};
   dim3 grid((unsigned)((I + 127) / 128), (unsigned)((J + 127) / 128), (unsigned)splits);
@@ -421,7 +459,7 @@ int tr_wgrad(const float* A, int lda, const float* B, int ldb, long rows, int b_
 int tr_colsum(const float* X, int ldx, long rows, int C, float* out, double* red, cudaStream_t st) {
   const int chunks = (int)((rows + kRedRows - 1) / kRedRows);
   RowGeom none{};
-  col_reduce_kernel<2><<<dim3(chunks, (C + 127) / 128), 128, 0, st>>>(X, ldx, nullptr, 0, nullptr, nullptr, rows, C, none, 0, red);
+  col_reduce_kernel<2><<<dim3(chunks, (C + 127) / 128), 128 * kRedLanes, 0, st>>>(X, ldx, nullptr, 0, nullptr, nullptr, rows, C, none, 0, red);
   col_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, chunks, C, 0, out);
   dan_count_launch(2);
   DAN_CUDA_TRY(cudaGetLastError());
@@ -500,7 +538,7 @@ int dan_train_forward_impl(dan_model* m, const dan_weights* w, const DevInputs& 
     float* Y = R_(pl.y[l], C);
     if (m->cfg.use_batchnorm) {
       double* mean = STATS + (size_t)l * 4 * C; double* rstd = mean + C;
-      col_reduce_kernel<0><<<dim3(pl.chunks, (C + 127) / 128), 128, 0, st>>>(U, C, nullptr, 0, nullptr, nullptr, rows, C, g, 1, RED);
+      col_reduce_kernel<0><<<dim3(pl.chunks, (C + 127) / 128), 128 * kRedLanes, 0, st>>>(U, C, nullptr, 0, nullptr, nullptr, rows, C, g, 1, RED);
       bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(RED, pl.chunks, C, N, mean, rstd, const_cast<float*>(w->bn_mean[l]), const_cast<float*>(w->bn_var[l]));
       bn_apply_kernel<<<grid1d(rows * C), 256, 0, st>>>(U, Y, mean, rstd, w->bn_w[l], w->bn_b[l], rows, C, g);
       dan_count_launch(3);
@@ -551,7 +589,7 @@ int dan_train_forward_impl(dan_model* m, const dan_weights* w, const DevInputs& 
     if (i == m->cfg.num_fc) { x = xd; break; }
     float* a = reinterpret_cast<float*>(base + pl.act[i]);
     const int Nf = m->cfg.fc_sizes[i];
-    if ((rc = tr_linear(xd, K, B, K, m->fcW[i], Nf, Nf, m->fcB[i], 1, nullptr, 0, a, Nf, st))) return rc;
+    if ((rc = tr_linear(xd, K, B, K, m->fcW[i], Nf, Nf, m->fcB[i], 1, nullptr, 0, a, Nf, reinterpret_cast<float*>(base + pl.tnpart), pl.tn_part_floats, st))) return rc;
     x = a; K = Nf;
   }
   float* HEADS = reinterpret_cast<float*>(base + pl.heads);
@@ -605,7 +643,7 @@ int dan_backward_impl(dan_model* m, const dan_weights* w, const DevInputs& in, c
   pad_rows_kernel<<<grid1d((long)DAN_HEAD_PAD * m->hidden), 256, 0, st>>>(w->head_w, WT, DAN_NUM_HEAD_OUTPUTS, DAN_HEAD_PAD, m->hidden);
   dan_count_launch();
   // d(xd_heads) = dz . W_heads     (W' = torch (27 -> 32, hidden) read as [k = head output][n = hidden])
-  if ((rc = tr_linear(DZ, DAN_HEAD_PAD, B, DAN_HEAD_PAD, WT, m->hidden, m->hidden, nullptr, 0, nullptr, 0, dA, m->hidden, st))) return rc;
+  if ((rc = tr_linear(DZ, DAN_HEAD_PAD, B, DAN_HEAD_PAD, WT, m->hidden, m->hidden, nullptr, 0, nullptr, 0, dA, m->hidden, TNP, pl.tn_part_floats, st))) return rc;
   // ---- FC trunk, last layer first ----
   int Nf = m->hidden;
   for (int i = nfc - 1; i >= 0; --i) {
@@ -620,7 +658,7 @@ int dan_backward_impl(dan_model* m, const dan_weights* w, const DevInputs& in, c
     if ((rc = tr_wgrad(dA, Nf, xd, K, B, 0, Nf, K, Kreal, G_(grads->fc_w[i]), Kreal, 1, TNP, pl.tn_part_floats, st))) return rc;
     if ((rc = tr_colsum(dA, Nf, B, Nf, G_(grads->fc_b[i]), RED, st))) return rc;
     // d(xd_i) = dpre . W_i: the torch weight (N, K) row-major is the K-major operand of this product; layer 0 has K = fcIn columns (ld fcIn) against fcInPad rows of xd
-    if ((rc = tr_linear(dA, Nf, B, Nf, w->fc_w[i], Kreal, Kreal, nullptr, 0, nullptr, 0, dB, K, st))) return rc;
+    if ((rc = tr_linear(dA, Nf, B, Nf, w->fc_w[i], Kreal, Kreal, nullptr, 0, nullptr, 0, dB, K, TNP, pl.tn_part_floats, st))) return rc;
     { float* t = dA; dA = dB; dB = t; }
     Nf = K;
   }
@@ -696,7 +734,7 @@ int dan_backward_impl(dan_model* m, const dan_weights* w, const DevInputs& in, c
     double* mean = STATS + (size_t)l * 4 * C; double* rstd = mean + C; double* dgamma = mean + 2 * C; double* dbeta = mean + 3 * C;
     float* DZl = const_cast<float*>(dY) == GA ? GB : GB;      // dZ always lands in GB (element-wise, in place when dY == GB)
     if (m->cfg.use_batchnorm) {
-      col_reduce_kernel<1><<<dim3(pl.chunks, (C + 127) / 128), 128, 0, st>>>(dY, C, U, C, mean, rstd, rows, C, g, 1, RED);
+      col_reduce_kernel<1><<<dim3(pl.chunks, (C + 127) / 128), 128 * kRedLanes, 0, st>>>(dY, C, U, C, mean, rstd, rows, C, g, 1, RED);
       col_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(RED, pl.chunks, C, 0, G_(grads->bn_b[l]), dbeta);
       col_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(RED, pl.chunks, C, 1, G_(grads->bn_w[l]), dgamma);
       dan_count_launch(3);
