@@ -54,12 +54,25 @@ __global__ void __launch_bounds__(128 * kRedLanes) col_reduce_kernel(const float
     part[((long)blockIdx.x * 2 + 1) * C + c] = a1;
   }
 }
-__global__ void bn_stats_finish_kernel(const double* __restrict__ part, int chunks, int C, double N, double* __restrict__ mean, double* __restrict__ rstd,
-                                       float* __restrict__ run_mean, float* __restrict__ run_var) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s0 = 0.0, s1 = 0.0;
-  for (int k = 0; k < chunks; ++k) { s0 += part[((long)k * 2 + 0) * C + c]; s1 += part[((long)k * 2 + 1) * C + c]; }
+// the partials of a column are added by 8 lanes (chunks k, k + 8, ...), lanes in a fixed order: one CTA of 128 x 8 threads per 128 columns
+constexpr int kFinLanes = 8;
+__device__ __forceinline__ void fin_sum(const double* __restrict__ part, int chunks, int C, int c, int lane, int tx, double (&sh)[2][kFinLanes][128], double& s0, double& s1) {
+  double a0 = 0.0, a1 = 0.0;
+  if (c < C)
+    for (int k = lane; k < chunks; k += kFinLanes) { a0 += part[((long)k * 2 + 0) * C + c]; a1 += part[((long)k * 2 + 1) * C + c]; }
+  sh[0][lane][tx] = a0; sh[1][lane][tx] = a1;
+  __syncthreads();
+  s0 = sh[0][0][tx]; s1 = sh[1][0][tx];
+#pragma unroll
+  for (int k = 1; k < kFinLanes; ++k) { s0 += sh[0][k][tx]; s1 += sh[1][k][tx]; }
+}
+__global__ void __launch_bounds__(128 * kFinLanes) bn_stats_finish_kernel(const double* __restrict__ part, int chunks, int C, double N, double* __restrict__ mean,
+                                                                          double* __restrict__ rstd, float* __restrict__ run_mean, float* __restrict__ run_var) {
+  __shared__ double sh[2][kFinLanes][128];
+  const int tx = threadIdx.x & 127, lane = threadIdx.x >> 7, c = blockIdx.x * 128 + tx;
+  double s0, s1;
+  fin_sum(part, chunks, C, c, lane, tx, sh, s0, s1);
+  if (lane != 0 || c >= C) return;
   const double m = s0 / N;
   double var = s1 / N - m * m;
   if (var < 0.0) var = 0.0;
@@ -70,13 +83,18 @@ __global__ void bn_stats_finish_kernel(const double* __restrict__ part, int chun
     run_var[c] = (1.f - kBnMomentum) * run_var[c] + kBnMomentum * (float)(var * N / (N - 1.0));
   }
 }
-__global__ void col_finish_kernel(const double* __restrict__ part, int chunks, int C, int which, float* __restrict__ out, double* __restrict__ out64 = nullptr) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  double s = 0.0;
-  for (int k = 0; k < chunks; ++k) s += part[((long)k * 2 + which) * C + c];
-  if (out) out[c] = (float)s;
-  if (out64) out64[c] = s;
+// out0 / out1: sums of partial 0 / 1 (either may be null); out64_*: the same in double
+__global__ void __launch_bounds__(128 * kFinLanes) col_finish_kernel(const double* __restrict__ part, int chunks, int C, float* __restrict__ out0, double* __restrict__ out64_0,
+                                                                     float* __restrict__ out1, double* __restrict__ out64_1) {
+  __shared__ double sh[2][kFinLanes][128];
+  const int tx = threadIdx.x & 127, lane = threadIdx.x >> 7, c = blockIdx.x * 128 + tx;
+  double s0, s1;
+  fin_sum(part, chunks, C, c, lane, tx, sh, s0, s1);
+  if (lane != 0 || c >= C) return;
+  if (out0) out0[c] = (float)s0;
+  if (out64_0) out64_0[c] = s0;
+  if (out1) out1[c] = (float)s1;
+  if (out64_1) out64_1[c] = s1;
 }
 
 // ------------------------------------------------------------------------------------------------ element-wise
@@ -346,10 +364,11 @@ inline int grid1d(long total, int block = 256) {
   return (int)(gsz < 1 ? 1 : (gsz > 148 * 16 ? 148 * 16 : gsz));
 }
 
-// row ranges of a weight-gradient product (sgemm_tn_kernel): two CTAs per SM on a 148-SM part once the problem is large enough
-inline int tn_splits(long rows) {
-  int splits = (int)(rows / 2048);
-  return splits < 1 ? 1 : (splits > 296 ? 296 : splits);
+// row ranges of a weight-gradient product (sgemm_tn_kernel): enough of them for two CTAs per SM of a 148-SM part, at least 256 rows each
+inline int tn_splits(long rows, int tiles) {
+  long splits = (296 + tiles - 1) / tiles;
+  if (splits > rows / 256) splits = rows / 256;
+  return splits < 1 ? 1 : (int)splits;
 }
 constexpr int kLinearMaxSplits = 40;
 
@@ -399,8 +418,7 @@ TrainPlan make_train_plan(const dan_model* m, int B) {
   pl.dhw = take((size_t)L * pl.hw_layer_stride * 4);
   pl.dfc[0] = take((size_t)pl.BPad * m->fcInPad * 4); pl.dfc[1] = take((size_t)pl.BPad * m->fcInPad * 4);
   pl.dz_heads = take((size_t)pl.BPad * DAN_HEAD_PAD * 4);
-  int splits = tn_splits(pl.rows);
-  pl.tn_part_floats = (size_t)splits * 128 * 128 + (size_t)64 * bott * g.pitch * bott;      // conv-shaped problems | compression (I = bott, J = P*bott)
+  pl.tn_part_floats = (size_t)296 * 128 * 128 + (size_t)64 * bott * g.pitch * bott;      // conv-shaped problems | compression (I = bott, J = P*bott)
   const size_t fc_part = (size_t)kLinearMaxSplits * pl.BPad * 1024;                          // split-K partials of the small-M FC products (tr_linear)
   if (pl.tn_part_floats < fc_part) pl.tn_part_floats = fc_part;
   pl.tnpart = take(pl.tn_part_floats * 4);
@@ -416,35 +434,43 @@ TrainPlan make_train_plan(const dan_model* m, int B) {
 
 int tr_gemm(const GemmParams& p, cudaStream_t st) { return launch_gemm(p, st); }
 
-// y = [relu](x W + b) for a row-major activation matrix x [M][lda] and a K-major weight W[k][n]. A batch-sized M with a long K (FC1:
-// 32 x 73 856 -> 1024) would run on N / 128 CTAs: such products go split-K over fixed K ranges (partials in `part`, added in order by
-// splitk_finish_kernel), enough ranges for two CTAs per SM.
-int tr_linear(const float* A, int lda, int M, int K, const float* W, int N, int ldw, const float* bias, int relu, const float* resid, int ldr, float* out, int ldo,
-              float* part, size_t part_floats, cudaStream_t st) {
-  GemmParams q{};
-  q.A = A; q.lda = lda; q.a_rows = M; q.M = M; q.ntaps = 1; q.tap_off[0] = 0; q.Kc = K;
-  q.W = W; q.N = N; q.ldw = ldw; q.bias = bias; q.relu = relu; q.resid = resid; q.ldr = ldr; q.out = out; q.ldo = ldo; q.splits = 1;
-  const int tiles = ((M + 127) / 128) * ((N + 127) / 128);
+// A product with few output tiles and a long K (FC1: 32 x 73 856 -> 1024; the (1 x 201) compression: 3200 x 6432 -> 32) would run on a
+// handful of CTAs: such products go split-K over fixed K ranges (partials in `part`, added in order by splitk_finish_kernel with the
+// bias / ReLU), enough ranges for two CTAs per SM. Anything with a row mask, BatchNorm fold, residual or head activation runs unsplit.
+int tr_gemm_auto(GemmParams q, float* part, size_t part_floats, cudaStream_t st) {
+  const int bn = q.N <= 32 ? 32 : 128;
+  const int tiles = ((q.M + 127) / 128) * ((q.N + bn - 1) / bn);
+  const int K = q.ntaps * q.Kc;
   int splits = 1;
-  if (part && !resid && tiles < 74 && K >= 4096) {
+  if (part && !q.resid && !q.scale && !q.head_act && q.mask_pitch == 0 && tiles < 74 && K >= 4096) {
     splits = (296 + tiles - 1) / tiles;
     if (splits > kLinearMaxSplits) splits = kLinearMaxSplits;
     if (splits > K / 64) splits = K / 64;
-    while (splits > 1 && (size_t)splits * M * N > part_floats) --splits;
+    while (splits > 1 && (size_t)splits * q.M * q.N > part_floats) --splits;
   }
   if (splits <= 1) return launch_gemm(q, st);
-  q.out = part; q.ldo = N; q.splits = splits; q.split_stride = (long)M * N; q.bias = nullptr; q.relu = 0;
+  const float* bias = q.bias; const int relu = q.relu; float* out = q.out; const int ldo = q.ldo;
+  q.out = part; q.ldo = q.N; q.splits = splits; q.split_stride = (long)q.M * q.N; q.bias = nullptr; q.relu = 0;
   int rc = launch_gemm(q, st);
   if (rc) return rc;
-  splitk_finish_kernel<<<grid_for((long)M * N), 256, 0, st>>>(part, splits, q.split_stride, M, N, N, bias, relu, 0, out, ldo);
+  splitk_finish_kernel<<<grid_for((long)q.M * q.N), 256, 0, st>>>(part, splits, q.split_stride, q.M, q.N, q.N, bias, relu, 0, out, ldo);
   dan_count_launch();
   DAN_CUDA_TRY(cudaGetLastError());
   return DAN_OK;
 }
 
+// y = [relu](x W + b) for a row-major activation matrix x [M][lda] and a K-major weight W[k][n]
+int tr_linear(const float* A, int lda, int M, int K, const float* W, int N, int ldw, const float* bias, int relu, const float* resid, int ldr, float* out, int ldo,
+              float* part, size_t part_floats, cudaStream_t st) {
+  GemmParams q{};
+  q.A = A; q.lda = lda; q.a_rows = M; q.M = M; q.ntaps = 1; q.tap_off[0] = 0; q.Kc = K;
+  q.W = W; q.N = N; q.ldw = ldw; q.bias = bias; q.relu = relu; q.resid = resid; q.ldr = ldr; q.out = out; q.ldo = ldo; q.splits = 1;
+  return tr_gemm_auto(q, part, part_floats, st);
+}
+
 // out[i * rs + j * cs] = sum_m A[m][i] * B[m + b_off][j]
 int tr_wgrad(const float* A, int lda, const float* B, int ldb, long rows, int b_off, int I, int J, int Jkeep, float* out, long rs, long cs, float* part, size_t part_floats, cudaStream_t st) {
-  int splits = tn_splits(rows);
+  int splits = tn_splits(rows, ((I + 127) / 128) * ((J + 127) / 128));
   while (splits > 1 && (size_t)splits * I * J > part_floats) --splits;
   TnParams p{A, lda, B, ldb, rows, b_off, I, J, part, splits, out, rs, cs, Jkeep};
   dim3 grid((unsigned)((I + 127) / 128), (unsigned)((J + 127) / 128), (unsigned)splits);
@@ -460,7 +486,7 @@ int tr_colsum(const float* X, int ldx, long rows, int C, float* out, double* red
   const int chunks = (int)((rows + kRedRows - 1) / kRedRows);
   RowGeom none{};
   col_reduce_kernel<2><<<dim3(chunks, (C + 127) / 128), 128 * kRedLanes, 0, st>>>(X, ldx, nullptr, 0, nullptr, nullptr, rows, C, none, 0, red);
-  col_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(red, chunks, C, 0, out);
+  col_finish_kernel<<<(C + 127) / 128, 128 * kFinLanes, 0, st>>>(red, chunks, C, out, nullptr, nullptr, nullptr);
   dan_count_launch(2);
   DAN_CUDA_TRY(cudaGetLastError());
   return DAN_OK;
@@ -539,7 +565,7 @@ int dan_train_forward_impl(dan_model* m, const dan_weights* w, const DevInputs& 
     if (m->cfg.use_batchnorm) {
       double* mean = STATS + (size_t)l * 4 * C; double* rstd = mean + C;
       col_reduce_kernel<0><<<dim3(pl.chunks, (C + 127) / 128), 128 * kRedLanes, 0, st>>>(U, C, nullptr, 0, nullptr, nullptr, rows, C, g, 1, RED);
-      bn_stats_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(RED, pl.chunks, C, N, mean, rstd, const_cast<float*>(w->bn_mean[l]), const_cast<float*>(w->bn_var[l]));
+      bn_stats_finish_kernel<<<(C + 127) / 128, 128 * kFinLanes, 0, st>>>(RED, pl.chunks, C, N, mean, rstd, const_cast<float*>(w->bn_mean[l]), const_cast<float*>(w->bn_var[l]));
       bn_apply_kernel<<<grid1d(rows * C), 256, 0, st>>>(U, Y, mean, rstd, w->bn_w[l], w->bn_b[l], rows, C, g);
       dan_count_launch(3);
     }
@@ -567,7 +593,7 @@ int dan_train_forward_impl(dan_model* m, const dan_weights* w, const DevInputs& 
       c.A = T; c.lda = g.pitch * bott; c.a_rows = (long)B * m->R; c.M = B * m->R; c.ntaps = 1; c.tap_off[0] = 0;
       c.Kc = g.P * bott; c.W = m->compW[l]; c.N = bott; c.ldw = bott; c.bias = m->compB[l];
       c.out = HW + (long)l * pl.hw_layer_stride; c.ldo = bott; c.splits = 1;
-      if ((rc = tr_gemm(c, st))) return rc;
+      if ((rc = tr_gemm_auto(c, reinterpret_cast<float*>(base + pl.tnpart), pl.tn_part_floats, st))) return rc;
     }
     DAN_CUDA_TRY(cudaGetLastError());
     cur = H; ld_cur = C;
@@ -735,9 +761,8 @@ int dan_backward_impl(dan_model* m, const dan_weights* w, const DevInputs& in, c
     float* DZl = const_cast<float*>(dY) == GA ? GB : GB;      // dZ always lands in GB (element-wise, in place when dY == GB)
     if (m->cfg.use_batchnorm) {
       col_reduce_kernel<1><<<dim3(pl.chunks, (C + 127) / 128), 128 * kRedLanes, 0, st>>>(dY, C, U, C, mean, rstd, rows, C, g, 1, RED);
-      col_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(RED, pl.chunks, C, 0, G_(grads->bn_b[l]), dbeta);
-      col_finish_kernel<<<(C + 127) / 128, 128, 0, st>>>(RED, pl.chunks, C, 1, G_(grads->bn_w[l]), dgamma);
-      dan_count_launch(3);
+      col_finish_kernel<<<(C + 127) / 128, 128 * kFinLanes, 0, st>>>(RED, pl.chunks, C, G_(grads->bn_b[l]), dbeta, G_(grads->bn_w[l]), dgamma);
+      dan_count_launch(2);
     }
     bn_relu_bwd_kernel<<<grid1d(rows * C), 256, 0, st>>>(dY, U, mean, rstd, w->bn_w[l], dgamma, dbeta, invN, DZl, rows, C, g, m->cfg.use_batchnorm);
     dan_count_launch();
