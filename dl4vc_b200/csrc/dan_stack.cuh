@@ -29,7 +29,7 @@
 // epilogue (relu, bf16, T store) runs under the conv MMAs instead of forming an op + epilogue round trip of its own.
 //
 // Per CTA: two independent read pipelines ("slots": own main accumulator, own epilogue warps, own issuer warp). ONE weight
-// ring (14 x 8 KB stages) feeds both: slot 1 runs one op behind slot 0 and every stage is consumed twice before it is
+// ring (7 x 16 KB stages) feeds both: slot 1 runs one op behind slot 0 and every stage is consumed twice before it is
 // refilled. Work is handed out in blocks of 20 reads of one candidate; a block with an odd number of reads is completed by
 // a phantom read (same op sequence, no global side effects), so both slots always run identical op sequences.
 #pragma once
@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     auto wait_dep = [&](bool first_of_read, uint32_t k) {
       // slot 1 starts op n only after slot 0 has issued all of its op n: the tensor pipe then runs slot 1's MMAs under slot 0's
       // epilogue (and vice versa) instead of both slots computing and then both draining, and the lag between the two
-      // consumers of the shared weight ring stays within one op (<= 13 of the 14 stages).
+      // consumers of the shared weight ring stays within one op (bottleneck + conv = all 7 stages).
       // (polled with a short sleep: a tight shared-memory spin would take issue slots from the epilogue warps of this warp's scheduler)
       STK_PROF(0);
       if (s == 1) { uint32_t spins = 0; while (*issued <= gops) { __nanosleep(32); if (++spins > (1u << 24)) __trap(); } }
