@@ -21,7 +21,7 @@ constexpr float kBnMomentum = 0.1f, kBnEps = 1e-5f;      // nn.BatchNorm2d defau
 
 // ------------------------------------------------------------------------------------------------ column reductions
 // part[chunk][which][c]: MODE 0: sum x | sum x^2 ; MODE 1: sum dy | sum dy * xhat, xhat = (u - mean) * rstd ; MODE 2: sum x
-constexpr int kRedLanes = 4;             // row lanes per column: threads (c, lane) walk rows lane, lane + 4, ... of the partial's range
+constexpr int kRedLanes = 8;             // row lanes per column: threads (c, lane) walk rows lane, lane + 8, ... of the partial's range
 template <int MODE>
 __global__ void __launch_bounds__(128 * kRedLanes) col_reduce_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ U, int ldu,
                                                                      const double* __restrict__ mean, const double* __restrict__ rstd, long rows, int C,
