@@ -147,6 +147,37 @@ def cpu_reference_rate(cfg, sd, sample, batch, repeats, warmup=1):
     return batch * len(times) / sum(times), times
 
 
+def torch_eager_gpu_rate(cfg, sd, sample, dev, batch=16, repeats=5):
+    """Second stated baseline: the reference's own op sequence (oracle/dan_torch_cpu.py) as torch eager kernels on this
+    GPU, fp32 with TF32 off — what running the reference's model.py on a B200 costs. A bounded sample; reported, not a target."""
+    import torch
+
+    from oracle import dan_torch_cpu
+
+    tf32 = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    try:
+        sd_dev = {k: (v.to(dev) if hasattr(v, "to") else torch.as_tensor(v).to(dev)) for k, v in sd.items()}
+        r, q, s, ref, rm, vm = [torch.from_numpy(a).to(dev) for a in sample.slice(0, batch).arrays()]
+        dan_torch_cpu.forward(cfg, sd_dev, r, ref, q, s, rm, vm)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(repeats):
+            dan_torch_cpu.forward(cfg, sd_dev, r, ref, q, s, rm, vm)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        return {"value": batch * repeats / (ms * 1e-3), "unit": UNIT, "kind": "reference op sequence as torch eager CUDA kernels (cuDNN / cuBLAS fp32, TF32 off)",
+                "sample": f"{repeats} timed batches x {batch} of the same dense PROD candidates (1 warm-up), torch {torch.__version__}"}
+    except Exception as exc:      # an out-of-memory or library failure of the baseline must not take the bench line down
+        return {"value": None, "error": f"{type(exc).__name__}: {str(exc)[:160]}"}
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = tf32
+        torch.cuda.empty_cache()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -498,6 +529,8 @@ def run_b200(args):
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"{reps} timed batches x {nb} = {reps * nb} of the same dense PROD candidates (1 warm-up), torch {torch.__version__} "
                                           f"CPU fp32, oracle/dan_torch_cpu.py = the reference's op sequence; batch times {['%.2f' % t for t in times]} s"}
+        if not args.no_eager_baseline:
+            line["torch_eager_gpu"] = torch_eager_gpu_rate(cfg, sd, sample, dev)
     print(json.dumps(line), flush=True)
     if dist is not None:
         dist.destroy_process_group()
@@ -516,6 +549,7 @@ def main():
     ap.add_argument("--mode", default="forward", choices=["forward", "train"], help="train: the data-parallel training step (BASELINE configs[4]) as its own line")
     ap.add_argument("--train-batch", type=int, default=32, help="candidates per training step per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true", help="skip the torch-eager-on-this-GPU sample of the reference op sequence")
     ap.add_argument("--no-fp32", action="store_true", help="skip the fp32 1e-4-parity path block (BASELINE configs[1])")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step block (BASELINE configs[4])")
     args = ap.parse_args()
