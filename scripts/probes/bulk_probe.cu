@@ -43,9 +43,9 @@ int main(int argc, char** argv) {
   long long* d; cudaMalloc(&d, 148 * 4 * 8);
   cudaFuncSetAttribute(probe, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
   struct C { int stage_bytes, stages, replicas, producers, mode, split, nowait; } cs[] = {
-    {8192, 7, 1, 2, 0, 1, 0}, {8192, 7, 1, 2, 0, 1, 1}, {8192, 7, 1, 2, 0, 4, 0}, {8192, 7, 1, 2, 0, 4, 1}, {8192, 7, 1, 2, 0, 16, 1}, {32768, 3, 1, 2, 0, 1, 1}, {8192, 7, 1, 4, 0, 1, 0},
+    {8192, 7, 1, 2, 0, 1, 0}, {8192, 7, 1, 2, 0, 1, 1}, {16384, 7, 1, 1, 0, 1, 0}, {16384, 3, 1, 2, 0, 1, 0}, {16384, 3, 4, 2, 0, 1, 0}, {16384, 3, 1, 2, 0, 4, 0}, {32768, 3, 1, 2, 0, 1, 0}, {8192, 5, 1, 4, 0, 1, 0},
   };
-  for (int grid : {148}) for (auto& c : cs) {
+  for (int grid : {1, 148}) for (auto& c : cs) {
     const int iters = 2000;
     probe<<<grid, 128, 200 * 1024>>>(w, region, c.replicas, region, c.stage_bytes, c.stages, c.producers, iters, c.mode, c.split, c.nowait, d);
     cudaError_t e = cudaDeviceSynchronize();
