@@ -804,7 +804,7 @@ int dan_bf16_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
   return DAN_OK;
 }
 
-// ---- test hook for the bit-exact encoding work: the fused kernel's encoder prologue (stk_enc_fetch / stk_enc_write, dan_stack.cuh)
+// ---- test hook for the bit-exact encoding work: the fused kernel's encoder prologue (stk_enc_fetch / stk_enc_rows / stk_enc_store, dan_stack.cuh)
 // run stand-alone, one CTA per read, its six input planes written out in the reference's logical order (B, Cin, R, P) as fp32
 namespace {
 __global__ void __launch_bounds__(kStkEpiThreads) stack_encode_dump_kernel(StackParams p, int Cin, float* __restrict__ out) {
@@ -812,7 +812,8 @@ __global__ void __launch_bounds__(kStkEpiThreads) stack_encode_dump_kernel(Stack
   const int r = blockIdx.x, pos = threadIdx.x;
   const long cand = blockIdx.y;
   const StkEncBytes eb = stk_enc_fetch(p, cand, r, pos);
-  stk_enc_write(p, cand, pos, 0, eb, buf);
+  const StkEncRows rows = stk_enc_rows(p, pos, 0, eb, stk_enc_fetch_cand(p, cand, pos));
+  stk_enc_store(p, pos, eb, rows, buf);
   __syncthreads();
   for (int i = threadIdx.x; i < Cin * p.P; i += blockDim.x) {
     const int c = i / p.P, pp = i - c * p.P;

@@ -173,7 +173,7 @@ __device__ __forceinline__ uint64_t stk_desc(uint32_t lo, uint32_t hi) { return 
 
 // ---- pileup encoder of one read (model.py:450-627,719), run by the 256 epilogue threads of a slot: thread t owns position t.
 // Bytes of the read (token, q-score, strand) are requested early (stk_enc_fetch) and turned into the six 8-channel planes of the
-// conv-1 input later (stk_enc_write):  0-19 E[tok]+pe | 20-39 E[ref]+pe | 40 q*0.01 | 41 strand*0.5 | 42 ref-match | 43 var-match |
+// conv-1 input later (stk_enc_rows / stk_enc_store):  0-19 E[tok]+pe | 20-39 E[ref]+pe | 40 q*0.01 | 41 strand*0.5 | 42 ref-match | 43 var-match |
 // 44 var-length (from the REF mask, model.py:579,584) | 45-47 zero. Integer work (agreement of the read with the ref / var
 // proposal over all 201 positions) is an AND-reduction over the slot's threads; the float channels come from a bf16 table of
 // E[tok] + pe[p] built once per weight load, so every value is bf16_rn of the reference's fp32 value.
@@ -188,23 +188,38 @@ __device__ __forceinline__ StkEncBytes stk_enc_fetch(const StackParams& p, long 
   return b;
 }
 
-__device__ __forceinline__ void stk_enc_write(const StackParams& p, long cand, int pos, int s, StkEncBytes eb, uint8_t* buf) {
-  const uint32_t tok = eb & 0xFFu, qv = (eb >> 8) & 0xFFu, sv = eb >> 16;
-  uint32_t refp = 0, rmk = 0, vmk = 0;
-  if (pos < p.P) { refp = __ldg(p.bytes.ref + cand * p.P + pos); rmk = __ldg(p.bytes.ref_masks + cand * p.P + pos); vmk = __ldg(p.bytes.var_masks + cand * p.P + pos); }
+// per-candidate bytes of position `pos` (the same for every read of the candidate): ref token | ref-mask << 8 | var-mask << 16
+__device__ __forceinline__ uint32_t stk_enc_fetch_cand(const StackParams& p, long cand, int pos) {
+  if (pos >= p.P) return 0u;
+  return (uint32_t)__ldg(p.bytes.ref + cand * p.P + pos) | (uint32_t)__ldg(p.bytes.ref_masks + cand * p.P + pos) << 8 | (uint32_t)__ldg(p.bytes.var_masks + cand * p.P + pos) << 16;
+}
+// The six 16-byte rows of position `pos` (one per input chunk plane). stk_enc_rows does the integer work and REQUESTS the table rows; it runs
+// while the buffer is still being read out by the TMA engine, and stk_enc_store writes the rows once the buffer is free: the two block-wide
+// reductions and the L2 latency of the table stay off the read-to-read chain.
+struct StkEncRows { uint4 r0, r1, r2, a0, a1, a2; uint32_t misc; };
+__device__ __forceinline__ StkEncRows stk_enc_rows(const StackParams& p, int pos, int s, StkEncBytes eb, uint32_t cb) {
+  const uint32_t tok = eb & 0xFFu, refp = cb & 0xFFu, rmk = (cb >> 8) & 0xFFu, vmk = cb >> 16;
   const bool agreeR = named_bar_and(1 + s, kStkEpiThreads, rmk == 0 || tok == rmk);       // model.py:592-593
   const bool agreeV = named_bar_and(1 + s, kStkEpiThreads, vmk == 0 || tok == vmk);       // model.py:607-608
+  StkEncRows e{};
   if (pos < p.P) {
     const uint4* tr = p.enc_tab + ((long)pos * DAN_VOCAB + min(tok, (uint32_t)DAN_VOCAB - 1)) * 3;
     const uint4* tf = p.enc_tab + ((long)pos * DAN_VOCAB + min(refp, (uint32_t)DAN_VOCAB - 1)) * 3;
-    const uint4 r0 = __ldg(tr), r1 = __ldg(tr + 1), r2 = __ldg(tr + 2), a0 = __ldg(tf), a1 = __ldg(tf + 1), a2 = __ldg(tf + 2);
-    const float m0 = (rmk != 0 && agreeR) ? 1.f : 0.f, m1 = (vmk != 0 && agreeV) ? 1.f : 0.f, m2 = rmk != 0 ? 1.f : 0.f;
+    e.r0 = __ldg(tr); e.r1 = __ldg(tr + 1); e.r2 = __ldg(tr + 2); e.a0 = __ldg(tf); e.a1 = __ldg(tf + 1); e.a2 = __ldg(tf + 2);
+    e.misc = (rmk != 0 && agreeR ? 1u : 0u) | (vmk != 0 && agreeV ? 2u : 0u) | (rmk != 0 ? 4u : 0u);
+  }
+  return e;
+}
+__device__ __forceinline__ void stk_enc_store(const StackParams& p, int pos, StkEncBytes eb, const StkEncRows& e, uint8_t* buf) {
+  if (pos < p.P) {
+    const uint32_t qv = (eb >> 8) & 0xFFu, sv = eb >> 16;
+    const float m0 = (e.misc & 1u) ? 1.f : 0.f, m1 = (e.misc & 2u) ? 1.f : 0.f, m2 = (e.misc & 4u) ? 1.f : 0.f;
     uint4* row = reinterpret_cast<uint4*>(buf + (size_t)(kStkLead + pos) * 16);
     constexpr int kPl = kStkPlane / 16;
-    row[0] = r0; row[kPl] = r1;
-    row[2 * kPl] = make_uint4(r2.x, r2.y, a0.x, a0.y);
-    row[3 * kPl] = make_uint4(a0.z, a0.w, a1.x, a1.y);
-    row[4 * kPl] = make_uint4(a1.z, a1.w, a2.x, a2.y);
+    row[0] = e.r0; row[kPl] = e.r1;
+    row[2 * kPl] = make_uint4(e.r2.x, e.r2.y, e.a0.x, e.a0.y);
+    row[3 * kPl] = make_uint4(e.a0.z, e.a0.w, e.a1.x, e.a1.y);
+    row[4 * kPl] = make_uint4(e.a1.z, e.a1.w, e.a2.x, e.a2.y);
     row[5 * kPl] = make_uint4(pack_bf16x2((float)qv * 0.01f, (float)sv * 0.5f), pack_bf16x2(m0, m1), pack_bf16x2(m2, 0.f), 0u);   // model.py:24,16
   }
 }
@@ -505,10 +520,10 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     // brings the read `it` of this slot into the buffer (or arranges for it): encode mode = synchronous (bytes fetched earlier);
     // planes mode = arm the barrier, lane 0 of every warp issues the bulk loads of two chunk planes (a bulk-copy instruction costs its
     // issuing thread ~170 cycles, so the 2 x kc_in of them are spread over the slot's 8 warps)
-    auto prepare_read = [&](const StkIter& it, StkEncBytes eb) {
+    auto prepare_read = [&](const StkIter& it, StkEncBytes eb, const StkEncRows& rows) {
       const bool valid = it.valid(p.R, s);
       if (p.in_mode == kStkInEncode) {
-        if (valid) stk_enc_write(p, p.cand0 + it.cand, gtid, s, eb, buf);   // both named-barrier reductions inside are warp-uniformly reached
+        if (valid) stk_enc_store(p, gtid, eb, rows, buf);
         fence_proxy_async_smem();
       } else {
         if (gtid == 0) mbar_expect_tx(&sm->in_full[s], valid ? plane_bytes * in_kc : 0u);
@@ -521,6 +536,14 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
             bulk_g2s_hint(dst + (size_t)kc * kStkPlane, src + kc * p.in_kstride, plane_bytes, &sm->in_full[s], once);
         }
       }
+    };
+    // encode mode: integer work + table requests of the read `it` (its bytes in eb); every thread of the slot takes part in the two named-barrier
+    // reductions, so the call is made slot-uniformly. cand_bytes caches the candidate-level bytes of this thread's position.
+    uint32_t cand_bytes = 0u; int cand_cached = -1;
+    auto encode_rows = [&](const StkIter& it, StkEncBytes eb) -> StkEncRows {
+      if (p.in_mode != kStkInEncode || it.done() || !it.valid(p.R, s)) return StkEncRows{};
+      if (it.cand != cand_cached) { cand_bytes = stk_enc_fetch_cand(p, p.cand0 + it.cand, gtid); cand_cached = it.cand; }
+      return stk_enc_rows(p, gtid, s, eb, cand_bytes);
     };
     auto fetch_read = [&](const StkIter& it) -> StkEncBytes {
       if (it.done() || !it.valid(p.R, s)) return 0u;
@@ -575,7 +598,7 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
     it.init(p.cands, p.R);
     if (!it.done()) {
       const StkEncBytes eb = fetch_read(it);
-      prepare_read(it, eb);
+      prepare_read(it, eb, encode_rows(it, eb));
     }
     mbar_arrive(&sm->act_ready[s]);       // initial credit: the issuer's first op waits for "phase 0"
     uint32_t opc = 0;
@@ -639,6 +662,11 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       // ---- the read's segment output is final: hand its planes to the TMA engine (store / read-axis reductions), under the last
       // bottleneck MMA / epilogue. Two chunk planes per warp (bulk groups are per thread: each issuer commits and waits for its own).
       named_bar_sync(1 + s, kStkEpiThreads);
+      // encode mode: the next read's integer work and table requests go out now, ahead of the output operations — their latency passes
+      // while the engine reads the buffer out, and only the six stores per position are left for the moment the buffer is free
+      StkIter nxt = it;
+      nxt.next(p.R);
+      const StkEncRows rows_next = encode_rows(nxt, eb_next);
       STK_PROF(10);
       if (lane == 0 && valid) {
         bulk_wait0();                                                     // earlier reductions into the same accumulators have landed (long ago)
@@ -664,8 +692,8 @@ __global__ void __launch_bounds__(kStkThreads, 1) dan_stack_kernel(const __grid_
       if (lane == 0) bulk_wait_read0();
       named_bar_sync(1 + s, kStkEpiThreads);
       STK_PROF(7);
-      it.next(p.R);
-      if (!it.done()) prepare_read(it, eb_next);
+      it = nxt;
+      if (!it.done()) prepare_read(it, eb_next, rows_next);
       STK_PROF(8);
       mbar_arrive(&sm->act_ready[s]);
       STK_PROF(12);
