@@ -22,6 +22,10 @@ struct Fp32Plan {
   int splits;
 };
 
+// The (1 x 201) compression is a K = 6432 product with one 32-column tile per 128 reads: a fixed number of K ranges (independent of the
+// batch shape, so results stay bitwise batch-invariant) brings a 148-candidate pass from 116 to 464 CTAs.
+constexpr int kCompSplitsFp32 = 4;
+
 Fp32Plan make_plan(const dan_model* m, int batch) {
   Fp32Plan pl{};
   pl.S = m->pass_candidates < batch ? m->pass_candidates : (batch > 0 ? batch : 1);
@@ -48,7 +52,10 @@ Fp32Plan make_plan(const dan_model* m, int batch) {
   }
   if (m->cfg.pool_combine_dimension > pl.maxN) pl.maxN = m->cfg.pool_combine_dimension;
   pl.splits = 16;
-  pl.off_part = take((size_t)pl.splits * BcPad * pl.maxN * 4);
+  size_t part_bytes = (size_t)pl.splits * BcPad * pl.maxN * 4;
+  const size_t comp_part = (size_t)kCompSplitsFp32 * pl.readsPad * (m->bott > 0 ? m->bott : 16) * 4;      // split-K partials of the (1 x 201) compression
+  if (comp_part > part_bytes) part_bytes = comp_part;
+  pl.off_part = take(part_bytes);
   pl.off_heads = take((size_t)BcPad * DAN_HEAD_PAD * 4);
   pl.total = off;
   return pl;
@@ -202,8 +209,11 @@ int dan_fp32_forward(dan_model* m, const DevInputs& in, int batch, float* heads_
           GemmParams c{};   // (1x201) compression = one long dot product per read (model.py:776)
           c.A = T; c.lda = g.pitch * bott; c.a_rows = (long)ns * m->R; c.M = ns * m->R; c.ntaps = 1; c.tap_off[0] = 0;
           c.Kc = g.P * bott; c.W = m->compW[l]; c.N = bott; c.ldw = bott; c.bias = m->compB[l];
-          c.out = HW + (long)l * pl.hw_layer_stride; c.ldo = bott; c.splits = 1;
+          float* hw_out = HW + (long)l * pl.hw_layer_stride;
+          c.bias = nullptr; c.out = PART; c.ldo = bott; c.splits = kCompSplitsFp32; c.split_stride = (long)c.M * bott;
           if ((rc = launch_gemm(c, st))) return rc;
+          splitk_finish_kernel<<<grid_for((long)c.M * bott), 256, 0, st>>>(PART, kCompSplitsFp32, c.split_stride, c.M, bott, bott, m->compB[l], 0, 0, hw_out, bott);
+          dan_count_launch();
         }
         cur = next; ld_cur = C; hsel = (hsel + 1) & 3;
       }
