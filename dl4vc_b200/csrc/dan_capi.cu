@@ -353,6 +353,45 @@ int dan_backward(dan_model* m, const dan_weights* params, const uint8_t* reads, 
   return dan_backward_impl(m, params, in, removed, batch, dropout_p, seed, dheads, heads_out, grads, tape, tape_bytes, static_cast<cudaStream_t>(stream));
 }
 
+namespace {
+// tools/format_vcf.py:107-138 per record; thresholds already resolved (dan_genotype_calls)
+__global__ void dan_genotype_calls_kernel(const float4* __restrict__ scores, const int32_t* __restrict__ ref_len, const int32_t* __restrict__ var_len, int batch,
+                                          dan_call_thresholds t, int8_t* __restrict__ gt_out, int32_t* __restrict__ q_out) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= batch) return;
+  const float4 s = scores[b];
+  // the script thresholds the "%.8f" text of the scores parsed back to double (utils.py:171-176, format_vcf.py:108)
+  const double nv = rint((double)s.y * 1e8) / 1e8, ov = rint((double)s.w * 1e8) / 1e8;
+  const int rl = ref_len[b], vl = var_len[b];
+  const bool snp = rl == 1 && vl == 1, lng = rl >= 3 || vl >= 3, del = rl > 1 && vl == 1;
+  const double thr = snp ? t.snp : (lng ? t.long_indel : (del ? t.del : t.indel));
+  const double hz = snp ? t.snp_zygo : (lng ? t.long_indel_zygo : (del ? t.del_zygo : t.indel_zygo));
+  const double margin = (1.0 - nv) - thr;
+  if (margin >= 0.0) {
+    gt_out[b] = ov >= hz ? 2 : 1;
+    q_out[b] = (int)(margin / (1.0 - thr) * 50.0);      // SCORE_BUCKETS, format_vcf.py:42,136-137
+  } else {
+    gt_out[b] = 0;
+    q_out[b] = -1;
+  }
+}
+}  // namespace
+
+int dan_genotype_calls(const float* scores, const int32_t* ref_len, const int32_t* var_len, int batch, const dan_call_thresholds* thr,
+                       int8_t* gt_out, int32_t* q_out, void* stream) {
+  if (batch < 0 || !thr || (batch > 0 && (!scores || !ref_len || !var_len || !gt_out || !q_out))) { dan_set_error("dan_genotype_calls: bad arguments"); return DAN_E_INVALID; }
+  if (batch == 0) return DAN_OK;
+  dan_call_thresholds t = *thr;                         // format_vcf.py:57-80
+  if (!(t.indel > 0.0)) { t.indel = t.snp; t.indel_zygo = t.snp_zygo; t.long_indel = t.indel; t.long_indel_zygo = t.indel_zygo; t.del = t.indel; t.del_zygo = t.indel_zygo; }
+  else {
+    if (!(t.long_indel > 0.0)) { t.long_indel = t.indel; t.long_indel_zygo = t.indel_zygo; }
+    if (!(t.del > 0.0)) { t.del = t.indel; t.del_zygo = t.indel_zygo; }
+  }
+  dan_genotype_calls_kernel<<<(batch + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<const float4*>(scores), ref_len, var_len, batch, t, gt_out, q_out);
+  DAN_CUDA_TRY(cudaGetLastError());
+  return DAN_OK;
+}
+
 int dan_scores(const float* heads, int batch, float* scores_out, void* stream) {
   if (batch < 0) { dan_set_error("negative batch"); return DAN_E_INVALID; }
   if (batch == 0) return DAN_OK;

@@ -124,6 +124,62 @@ def scores_on_device(heads: torch.Tensor) -> torch.Tensor:
     return out
 
 
+CALL_THRESHOLD_FIELDS = ("snp", "snp_zygo", "indel", "indel_zygo", "long_indel", "long_indel_zygo", "delete", "delete_zygo")
+
+
+def resolve_call_thresholds(snp=0.3, snp_zygo=0.5, indel=0.0, indel_zygo=0.5, long_indel=0.0, long_indel_zygo=0.5, delete=0.0, delete_zygo=0.5):
+    """The threshold fall-backs of tools/format_vcf.py:57-80 (arguments = its command-line options, same defaults). The script leaves the
+    delete pair unassigned when --indel_threshold is not given (and raises on the first short delete); here it follows the indel pair."""
+    if not indel > 0.0:
+        indel, indel_zygo = snp, snp_zygo
+        long_indel, long_indel_zygo = indel, indel_zygo
+        delete, delete_zygo = indel, indel_zygo
+    else:
+        if not long_indel > 0.0:
+            long_indel, long_indel_zygo = indel, indel_zygo
+        if not delete > 0.0:
+            delete, delete_zygo = indel, indel_zygo
+    return (snp, snp_zygo, indel, indel_zygo, long_indel, long_indel_zygo, delete, delete_zygo)
+
+
+def genotype_calls(scores, ref_len, var_len, **thresholds):
+    """Host restatement of the per-record part of tools/format_vcf.py:107-138, vectorised: (gt, q) with gt 0 = dropped, 1 = "0/1", 2 = "1/1"
+    and q the script's quality bucket (-1 when dropped). `scores` (n, 4) = [BP, NV, HV, OV] as written into the VCF ("%.8f")."""
+    t = resolve_call_thresholds(**thresholds)
+    s = np.asarray(scores, dtype=np.float32)
+    nv = np.rint(s[:, 1].astype(np.float64) * 1e8) / 1e8
+    ov = np.rint(s[:, 3].astype(np.float64) * 1e8) / 1e8
+    rl, vl = np.asarray(ref_len), np.asarray(var_len)
+    snp, lng, dele = (rl == 1) & (vl == 1), (rl >= 3) | (vl >= 3), (rl > 1) & (vl == 1)
+    thr = np.where(snp, t[0], np.where(lng, t[4], np.where(dele, t[6], t[2])))
+    hz = np.where(snp, t[1], np.where(lng, t[5], np.where(dele, t[7], t[3])))
+    margin = (1.0 - nv) - thr
+    keep = margin >= 0.0
+    gt = np.where(keep, np.where(ov >= hz, 2, 1), 0).astype(np.int8)
+    q = np.where(keep, (margin / (1.0 - thr) * 50.0).astype(np.int64), -1).astype(np.int32)
+    return gt, q
+
+
+def genotype_calls_on_device(scores: torch.Tensor, ref_len: torch.Tensor, var_len: torch.Tensor, **thresholds):
+    """Device version through the C-ABI (`dan_genotype_calls`): scores (B,4) CUDA float32 from `scores_on_device`, allele lengths (B,) int32
+    CUDA tensors -> (gt int8, q int32) CUDA tensors. No CPU path."""
+    import ctypes as C
+    from . import _lib
+    if not scores.is_cuda:
+        raise RuntimeError("genotype_calls_on_device needs CUDA tensors (no CPU path; genotype_calls is the host restatement)")
+    B = scores.shape[0]
+    scores = scores.contiguous().float()
+    rl = ref_len.to(device=scores.device, dtype=torch.int32).contiguous(); vl = var_len.to(device=scores.device, dtype=torch.int32).contiguous()
+    gt = torch.empty(B, dtype=torch.int8, device=scores.device); q = torch.empty(B, dtype=torch.int32, device=scores.device)
+    d = dict(zip(CALL_THRESHOLD_FIELDS, (0.3, 0.5, 0.0, 0.5, 0.0, 0.5, 0.0, 0.5)))
+    d.update(thresholds)
+    thr = (C.c_double * 8)(*[d[k] for k in CALL_THRESHOLD_FIELDS])
+    with torch.cuda.device(scores.device):
+        _lib.check(_lib.load_library().dan_genotype_calls(scores.data_ptr(), rl.data_ptr(), vl.data_ptr(), B, C.cast(thr, C.c_void_p), gt.data_ptr(), q.data_ptr(),
+                                                           torch.cuda.current_stream().cuda_stream), "dan_genotype_calls")
+    return gt, q
+
+
 def format_vcf_info(bin_score, vt_probs):
     """The strings utils.append_vcf_records writes into VCF column 3 (utils.py:171-176), vectorised over the batch."""
     b = np.asarray(bin_score, dtype=np.float64)

@@ -137,6 +137,24 @@ int dan_forward_host(dan_model* m, int precision, const uint8_t* reads, const ui
 #define DAN_NUM_SCORE_OUTPUTS 4
 int dan_scores(const float* heads, int batch, float* scores_out, void* stream);
 
+/* Replaces the per-record thresholding of tools/format_vcf.py (filter_format_vcf, :107-138) for a batch, on the device, so that a caller
+ * can drop the records that will not be written before their scores cross PCIe. For candidate b with scores row
+ * { BP, NV, HV, OV } (dan_scores) and allele lengths ref_len[b] / var_len[b] (the REF / ALT columns of its VCF record):
+ *   class: SNP (1/1), long indel (either allele >= 3 bases), short delete (ref > 1, alt == 1), other indel; the class picks the
+ *   call threshold and the homozygous threshold;  margin = (1 - NV) - threshold;  margin < 0 -> gt_out[b] = 0, q_out[b] = -1;
+ *   else gt_out[b] = 2 ("1/1") if OV >= homozygous threshold else 1 ("0/1"), q_out[b] = int(margin / (1 - threshold) * 50).
+ * NV and OV are first rounded to 8 decimals, the values the script parses back from the "%.8f" text of utils.py:171-176, and the
+ * arithmetic is double like Python's, so the integers match the script's. Thresholds are the script's command-line values;
+ * non-positive indel / long-indel / delete call thresholds fall back as format_vcf.py:57-80 does (long indel -> indel -> SNP; the script
+ * leaves the delete threshold unassigned when --indel_threshold is not given and raises on the first short delete: here it falls back
+ * to the indel pair). The script's merge of several records at one position (:150-215) works on sorted text and stays with the caller.
+ * scores, ref_len, var_len, gt_out, q_out: DEVICE pointers. */
+typedef struct dan_call_thresholds {
+  double snp, snp_zygo, indel, indel_zygo, long_indel, long_indel_zygo, del, del_zygo;
+} dan_call_thresholds;
+int dan_genotype_calls(const float* scores, const int32_t* ref_len, const int32_t* var_len, int batch, const dan_call_thresholds* thr,
+                       int8_t* gt_out, int32_t* q_out, void* stream);
+
 /* Replaces the per-record string formatting of utils.append_vcf_records (dl4vc/utils.py:171-176) for a batch: for each of the n
  * rows of `scores` (HOST pointer, n*4 fp32 as written by dan_scores) writes the fixed-width, NUL-terminated text
  * "BP=%.8f;NV=%.8f;HV=%.8f;OV=%.8f" at out + i*DAN_VCF_INFO_STRIDE (HOST buffer of n*DAN_VCF_INFO_STRIDE bytes). Values are

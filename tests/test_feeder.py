@@ -147,3 +147,35 @@ def test_decode_records_matches_reference_loader():
     assert np.array_equal(again.reads.numpy(), got["reads"])
     other, _ = decode_records(rf, np.arange(n), HostBatch(n, pin=False), seed=6, strict=False)
     assert not np.array_equal(other.reads.numpy()[deep], got["reads"][deep])
+
+
+def _call_golden():
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "genotype_calls.npz"))
+    names = ("snp", "snp_zygo", "indel", "indel_zygo", "long_indel", "long_indel_zygo", "delete", "delete_zygo")
+    sets = []
+    for k in range(int(g["num_sets"])):
+        ok = g["defined0"] if k == 0 else np.ones(len(g["scores"]), bool)      # the script raises on short deletes with its default thresholds
+        sets.append((dict(zip(names, g["thr%d" % k].tolist())), g["gt%d" % k], g["q%d" % k], ok))
+    return g["scores"], g["ref_len"], g["var_len"], sets
+
+
+def test_genotype_calls_match_reference_format_vcf():
+    """Host restatement of tools/format_vcf.py:107-138 against the real script run on 3000 scored records (oracle/make_call_goldens.py)."""
+    from dl4vc_b200.feeder import genotype_calls
+    scores, rl, vl, sets = _call_golden()
+    for thr, gt, q, ok in sets:
+        got_gt, got_q = genotype_calls(scores, rl, vl, **thr)
+        assert np.array_equal(got_gt[ok], gt[ok]) and np.array_equal(got_q[ok], q[ok])
+
+
+@pytest.mark.gpu
+def test_genotype_calls_on_device_match_reference_format_vcf():
+    import torch
+    from dl4vc_b200.feeder import genotype_calls_on_device
+    scores, rl, vl, sets = _call_golden()
+    dev = torch.device("cuda", 0)
+    s = torch.from_numpy(scores).to(dev); r = torch.from_numpy(rl).to(dev); v = torch.from_numpy(vl).to(dev)
+    for thr, gt, q, ok in sets:
+        got_gt, got_q = genotype_calls_on_device(s, r, v, **thr)
+        assert np.array_equal(got_gt.cpu().numpy()[ok], gt[ok]) and np.array_equal(got_q.cpu().numpy()[ok], q[ok])
