@@ -392,6 +392,61 @@ int dan_genotype_calls(const float* scores, const int32_t* ref_len, const int32_
   return DAN_OK;
 }
 
+namespace {
+// 8 independent FFMA chains per thread, 4096 FFMAs per chain and call
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* __restrict__ sink, int reps) {
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = (float)(threadIdx.x + i) * 1e-3f;
+  const float m = 1.0000001f, c = 1e-7f;
+  for (int r = 0; r < reps; ++r) {
+#pragma unroll
+    for (int k = 0; k < 512; ++k) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fmaf(a[i], m, c);
+    }
+  }
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += a[i];
+  if (t == 12345.678f) sink[0] = t;
+}
+}  // namespace
+
+double dan_measure_fma_tflops(double ms, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  int dev = 0, sms = 0;
+  float* sink = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  double result = -1.0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1.0;
+  if (cudaMalloc(&sink, 4) != cudaSuccess) return -1.0;
+  if (cudaEventCreate(&e0) == cudaSuccess && cudaEventCreate(&e1) == cudaSuccess) {
+    const int blocks = sms * 8;
+    auto run = [&](int reps) -> double {
+      cudaEventRecord(e0, st);
+      fma_peak_kernel<<<blocks, 256, 0, st>>>(sink, reps);
+      cudaEventRecord(e1, st);
+      if (cudaEventSynchronize(e1) != cudaSuccess) return -1.0;
+      float t = 0.f;
+      cudaEventElapsedTime(&t, e0, e1);
+      return (double)t;
+    };
+    const double flop_per_rep = 2.0 * 8 * 512 * 256.0 * blocks;
+    double t = run(8);                                     // warm-up and calibration
+    if (t > 0.0) {
+      int reps = (int)(8.0 * (ms > 1.0 ? ms : 1.0) / t) + 1;
+      if (reps > 1 << 20) reps = 1 << 20;
+      t = run(reps);
+      if (t > 0.0) result = flop_per_rep * reps / (t * 1e-3) / 1e12;
+    }
+  }
+  if (e0) cudaEventDestroy(e0);
+  if (e1) cudaEventDestroy(e1);
+  cudaFree(sink);
+  return result;
+}
+
 int dan_scores(const float* heads, int batch, float* scores_out, void* stream) {
   if (batch < 0) { dan_set_error("negative batch"); return DAN_E_INVALID; }
   if (batch == 0) return DAN_OK;

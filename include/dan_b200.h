@@ -274,6 +274,12 @@ int dan_debug_fc_input(dan_model* m, int precision, int batch, const void* works
 /* Kernel launches issued by the last dan_forward on this thread (for the benchmark's gpu_launches claim). */
 int dan_last_launch_count(void);
 
+/* Measurement aid for bench.py: the fp32 FMA rate this GPU sustains (TFLOP/s, 2 FLOP per FFMA) — a register-resident FFMA loop on every SM for
+ * about `ms` milliseconds, timed with CUDA events on `stream`. The fp32 parity path and the training kernels run on this pipe; bench.py reports
+ * this sustained figure (a pure FFMA loop is power-limited: ~54 of the nominal 74 TFLOP/s on B200) beside the nominal peak. Returns a negative
+ * value on a CUDA error. */
+double dan_measure_fma_tflops(double ms, void* stream);
+
 /* Measurement hook (bench.py roofline): when enabled, every kernel launch of dan_forward is bracketed by CUDA
  * events on the launching stream, grouped in DAN_PROF_* classes. dan_profile_enable(1) also clears earlier
  * spans. dan_profile_read waits for the recorded events and returns the number of spans; ms_by_class /
