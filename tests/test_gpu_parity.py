@@ -425,3 +425,34 @@ def test_capi_rejects_bad_calls():
     bad.total_conv_layers = 99
     hh = C.c_void_p()
     assert lib.dan_model_create(C.byref(bad), C.byref(hh)) == -2 and not hh.value
+
+
+def test_bf16_full_size_step_is_reproducible_and_candidate_order_independent():
+    """BASELINE's bench step (4144 PROD candidates per GPU) through size-independent properties: the same batch twice gives bitwise the
+    same head matrix, a permutation of the candidates permutes the rows bitwise (no cross-candidate op in the eval forward, SURVEY 8e;
+    fixed split-K ranges, ordered partial sums), and the first 148 rows equal a 148-candidate call of their own."""
+    from dl4vc_b200.config import prod_config
+    cfg = prod_config()
+    model = build_model(cfg, synth_state_dict(cfg, seed=1), precision="bf16")
+    uniq = make_pileups(259, seed=77, coverage="poisson")
+    reps = 16                                                   # 259 x 16 = 4144
+    arrays = [np.concatenate([a] * reps, axis=0) for a in uniq.arrays()]
+    dev = torch.device("cuda", 0)
+    t = [torch.from_numpy(np.ascontiguousarray(a)).to(dev) for a in arrays]
+    r, q, s, ref, rm, vm = t
+    first = model.forward_heads(r, ref, q, s, rm, vm)
+    again = model.forward_heads(r, ref, q, s, rm, vm)
+    assert torch.equal(first, again)
+    assert torch.equal(first[:259], first[259:518])             # the tiled copies of a candidate score identically wherever they sit
+    perm = torch.from_numpy(np.random.default_rng(5).permutation(4144)).to(dev)
+    shuffled = model.forward_heads(r[perm], ref[perm], q[perm], s[perm], rm[perm], vm[perm])
+    assert torch.equal(shuffled, first[perm])
+    small = model.forward_heads(r[:148], ref[:148], q[:148], s[:148], rm[:148], vm[:148])
+    assert torch.equal(small, first[:148])
+    assert torch.isfinite(first).all()
+
+
+def test_fma_rate_probe_returns_a_plausible_number():
+    from dl4vc_b200 import _lib
+    v = float(_lib.load_library().dan_measure_fma_tflops(5.0, torch.cuda.current_stream().cuda_stream))
+    assert 10.0 < v < 200.0
