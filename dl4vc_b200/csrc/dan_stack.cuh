@@ -46,7 +46,7 @@ constexpr int kStkBuf = kKC * kStkPlane;       // bytes per read buffer (54272)
 constexpr int kStkStageBytes = 16384;  // weight-ring stage = four k-step blocks of 4 KB
 constexpr int kStkStages = 7;          // stages of the weight ring shared by the two slots (>= the largest op: bottleneck 1 + conv 6)
 constexpr int kStkMaxSeg = 8;          // layers per segment
-constexpr int kStkRegsIssue = 56, kStkRegsEpi = 104;   // setmaxnreg redistributes the launch allocation (640 x 96): 128 x 56 + 512 x 104 = 60416 <= 61440
+constexpr int kStkRegsIssue = 64, kStkRegsEpi = 104;   // setmaxnreg redistributes the launch allocation (640 x 96 = 61440): 128 x 64 + 512 x 104 = 61440
 constexpr int kStkBmapChunk = 64;       // uint4 per (role, 16-position chunk) of the pool bias map: 32 lanes x 2 (bmap_pack_kernel, dan_bf16.cu)
 constexpr int kStkBmapPerCand = 8 * 7 * kStkBmapChunk;   // uint4 per candidate: 8 roles (position half, lane quadrant) x 7 chunks
 constexpr int kStkBott = 32;            // bottleneck width the fused kernel is built for (PROD; other widths take the layer-wise path)
