@@ -147,7 +147,7 @@ def cpu_reference_rate(cfg, sd, sample, batch, repeats, warmup=1):
     return batch * len(times) / sum(times), times
 
 
-def torch_eager_gpu_rate(cfg, sd, sample, dev, batch=16, repeats=5):
+def torch_eager_gpu_rate(cfg, sd, sample, dev, batch=16, repeats=10, warmup=4):
     """Second stated baseline: the reference's own op sequence (oracle/dan_torch_cpu.py) as torch eager kernels on this
     GPU, fp32 with TF32 off — what running the reference's model.py on a B200 costs. A bounded sample; reported, not a target."""
     import torch
@@ -160,7 +160,8 @@ def torch_eager_gpu_rate(cfg, sd, sample, dev, batch=16, repeats=5):
     try:
         sd_dev = {k: (v.to(dev) if hasattr(v, "to") else torch.as_tensor(v).to(dev)) for k, v in sd.items()}
         r, q, s, ref, rm, vm = [torch.from_numpy(a).to(dev) for a in sample.slice(0, batch).arrays()]
-        dan_torch_cpu.forward(cfg, sd_dev, r, ref, q, s, rm, vm)
+        for _ in range(warmup):          # the GPU has idled through the CPU baseline: library initialisation and the clock ramp stay outside
+            dan_torch_cpu.forward(cfg, sd_dev, r, ref, q, s, rm, vm)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -170,7 +171,7 @@ def torch_eager_gpu_rate(cfg, sd, sample, dev, batch=16, repeats=5):
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1)
         return {"value": batch * repeats / (ms * 1e-3), "unit": UNIT, "kind": "reference op sequence as torch eager CUDA kernels (cuDNN / cuBLAS fp32, TF32 off)",
-                "sample": f"{repeats} timed batches x {batch} of the same dense PROD candidates (1 warm-up), torch {torch.__version__}"}
+                "sample": f"{repeats} timed batches x {batch} of the same dense PROD candidates ({warmup} warm-up), torch {torch.__version__}"}
     except Exception as exc:      # an out-of-memory or library failure of the baseline must not take the bench line down
         return {"value": None, "error": f"{type(exc).__name__}: {str(exc)[:160]}"}
     finally:
